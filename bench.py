@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py -- agent-steps/sec of the per-timestep agent update (query + Zanlungo + integrate).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c3|c4|c2] [--variant ...]
+
+One JSON line on stdout (rank 0).  A "step" is one pass of the whole hot path (LocationHash2D rebuild,
+radius query, Zanlungo force, Euler integration) over the synthetic crowd.
+
+Workloads (BASELINE.json configs):
+  N = 1 : C3 -- 2^20 agents, uniform density 1/m^2 (jittered lattice), Zanlungo, shuffled ids.
+  N > 1 : C4 -- 2^24 agents total, spatial strips over the N GPUs (strong scaling).
+The shuffled crowd is timed in frozen-snapshot mode (RCS_STEP_NO_COMMIT): the reference model itself drives
+a dense mixed bidirectional crowd non-finite within 3-23 steps, so every timed step
+runs the full pipeline on the same physical snapshot and discards the result.  `--variant lane` times the
+lane-ordered crowd with committed steps instead (force pass idle).
+
+The reference arm (--impl reference) and the cpu_baseline leg time the CPU oracle in its literal
+data-structure form (hash maps, in-loop index update, map iteration order), single-threaded like the
+reference, on a bounded sub-crowd of the same density and planner.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_ZANLUNGO = 88  # read x,y,vx,vy,pvx,pvy + id, write x,y,vx,vy
+ALGO_BYTES_NOLOCALPLAN = 64
+L2_FLUSH_BYTES = 512 << 20
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the GPU is under load."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.lines: list[str] = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+                power.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_scene(workload: str, variant: str, lp_none: bool = False):
+    from rmf_crowdsim_b200 import scenes as SC
+
+    lp = ("none",) if lp_none else None
+    if workload == "c2":
+        sc = SC.config_c2(variant)
+        if lp_none:
+            sc.lp = ("none",)
+        return sc
+    if workload == "c3":
+        return SC.config_c3(variant, lp=lp)
+    if workload == "c4":
+        sc = SC.config_c4(variant)
+        if lp_none:
+            sc.lp = ("none",)
+        return sc
+    if workload.startswith("side"):
+        return SC.uniform_crowd(int(workload[4:]), variant, margin=64.0, lp=lp)
+    raise SystemExit(f"unknown workload {workload}")
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU oracle legs (cpu_baseline and --impl reference).  The only places bench.py executes oracle/.
+# --------------------------------------------------------------------------------------------------
+def oracle_run(scene, steps: int, warmup: int):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_ffi as O
+
+    o = O.OracleSim(scene.width, scene.height, scene.cell, scene.offset, index_mode=O.IN_LOOP,
+                    iter_order=O.MAP_ORDER, canonical=False)
+    hl = o.hl_parity(scene.hl[1])
+    lp = o.lp_none() if scene.lp[0] == "none" else o.lp_zanlungo(*scene.lp[1:])
+    ids = o.add_agents(scene.xy, hl, lp, scene.eyesight)
+
+    def inject():
+        o.set_state(ids, scene.xy[:, 0], scene.xy[:, 1], scene.vxy[:, 0], scene.vxy[:, 1])
+
+    total = 0.0
+    for k in range(warmup + steps):
+        inject()  # frozen snapshot: every step sees the same crowd (not timed)
+        t0 = time.perf_counter()
+        o.step(*scene.dt)
+        t1 = time.perf_counter()
+        if k >= warmup:
+            total += t1 - t0
+    return scene.n * steps / total, total
+
+
+def cpu_sample_scene(workload: str, variant: str, budget_steps: int):
+    """Bounded sample of the workload for the CPU legs: a sub-crowd of the same density, spacing and
+    planner, sized for ~1.7 s/step on one core (the literal data structures cost ~16 us per agent-step)."""
+    from rmf_crowdsim_b200 import scenes as SC
+
+    side = 320 if budget_steps <= 16 else (224 if budget_steps <= 40 else 128)
+    sc = SC.uniform_crowd(side, variant, margin=64.0)
+    return sc, f"{side * side}-agent sub-crowd of {workload} (same density 1/m^2, R=2 m, Zanlungo params), frozen snapshot"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    workload = args.workload or ("c3" if args.gpus == 1 else "c4")
+    scene, sample = cpu_sample_scene(workload, args.variant, args.steps + args.warmup)
+    value, total = oracle_run(scene, args.steps, max(args.warmup, 1))
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": "agent-steps/sec (query+Zanlungo+integrate)", "value": value,
+        "unit": "agent-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(workload, args.variant), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores_available": cores,
+                         "note": "C++ restatement of the reference CPU path (the Rust reference cannot be built "
+                                 "here: no rustc/cargo); single-threaded like the reference"},
+        "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(workload: str, variant: str) -> str:
+    names = {
+        "c2": "C2: 10,000 agents, 100x100 m, density 1/m^2, Zanlungo",
+        "c3": "C3: 2^20 agents, 1024x1024 m, density 1/m^2 (jittered lattice), Zanlungo, R=cell=2 m",
+        "c4": "C4: 2^24 agents, 4096x4096 m bidirectional +-x flow by id parity, spatial strips",
+    }
+    return names.get(workload, workload) + f", ids {variant}"
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def run_gpu_single(args):
+    import ctypes as C
+
+    from rmf_crowdsim_b200 import Duration, _native as N
+    from rmf_crowdsim_b200 import scenes as SC
+
+    workload = args.workload or "c3"
+    scene = make_scene(workload, args.variant, lp_none=args.no_local_plan)
+    frozen = args.variant == "shuffled" and not args.no_local_plan
+    dt = Duration(*scene.dt)
+    sim = SC.build_simulation(scene, device=0)
+    lib, h = sim._lib, sim._h
+    n = scene.n
+    state_bytes = n * 48 * 2
+    flush = state_bytes < (1 << 30)
+
+    def one_step():
+        N.check(h, lib.rcs_step_async(h, dt.secs, dt.nanos, N.RCS_STEP_NO_COMMIT if frozen else N.RCS_STEP_DEFAULT))
+
+    clocks = ClockSampler(0)
+    # warm-up: W steps, then keep stepping for ~0.4 s so the clock samples are taken under load
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    sim.sync()
+    clocks.start()
+    t_end = time.time() + 0.4
+    while time.time() < t_end:
+        for _ in range(8):
+            one_step()
+        sim.sync()
+
+    # timed region: K steps, each bracketed by events on the launching stream, L2 flushed in between
+    launches0 = sim.launch_count()
+    N.check(h, lib.rcs_kernel_timing(h, 1))
+    sim.sync()
+    wall0 = time.perf_counter()
+    total_ms = 0.0
+    K = args.steps
+    done = 0
+    while done < K:
+        batch = min(K - done, N.RCS_NUM_EVENTS // 2)
+        for b in range(batch):
+            if flush:
+                sim.flush_l2(L2_FLUSH_BYTES)
+            sim.event_record(2 * b)
+            one_step()
+            sim.event_record(2 * b + 1)
+        sim.sync()
+        for b in range(batch):
+            total_ms += sim.event_elapsed_ms(2 * b, 2 * b + 1)
+        done += batch
+    wall1 = time.perf_counter()
+    kt_ms, kt_n = C.c_double(), C.c_uint64()
+    N.check(h, lib.rcs_kernel_time_ms(h, C.byref(kt_ms), C.byref(kt_n)))
+    N.check(h, lib.rcs_kernel_timing(h, 0))
+    flush_launches = K if flush else 0
+    launches = sim.launch_count() - launches0 - flush_launches
+    st = sim.stats()
+    value = n * K / (total_ms * 1e-3)
+
+    # end to end through the C ABI with HOST buffers: every step uploads the preferred velocities of a host
+    # HighLevelPlanner (pinned), runs the step, and reads back x,y,vx,vy of every agent (pinned).
+    e2e = run_e2e(scene, frozen, min(K, 10), max(3, min(args.warmup, 5)))
+    clk = clocks.stop()
+
+    peaks, how = measured_peaks()
+    algo = ALGO_BYTES_NOLOCALPLAN if args.no_local_plan else ALGO_BYTES_ZANLUNGO
+    k_ms = kt_ms.value / max(kt_n.value, 1)
+    achieved = algo * n / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.exists(tp):
+        try:
+            with open(tp) as f:
+                traffic = json.load(f).get(f"{workload}_{args.variant}" + ("_nolp" if args.no_local_plan else ""))
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "hbm", "kernel": "step_kernel (radius query + Zanlungo + Euler, fused)",
+        "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "peak_source": how, "traffic": traffic,
+        "algorithmic_bytes_per_agent_step": algo, "kernel_ms": k_ms, "kernel_share_of_step": k_ms * K / total_ms,
+        "note": "the Zanlungo kernel is FP64-pipe-bound, not HBM-bound (SURVEY.md 8d); see fp64 keys",
+    }
+    fp64 = fp64_info(args)
+    if fp64:
+        roofline["fp64_peak_tflops_measured"] = fp64
+
+    sample_scene, sample = cpu_sample_scene(workload, args.variant, 6)
+    if args.no_local_plan:
+        sample_scene.lp = ("none",)
+    cpu_v, _ = oracle_run(sample_scene, 5, 1)
+    line = {
+        "metric": "agent-steps/sec (query+Zanlungo+integrate)", "value": value, "unit": "agent-steps/s",
+        "n_gpus": 1, "steps": K, "warmup": args.warmup, "ms_per_step": total_ms / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": workload_name(workload, args.variant) + (", NoLocalPlan" if args.no_local_plan else ""),
+            "agents": n, "mode": "frozen snapshot (RCS_STEP_NO_COMMIT)" if frozen else "committed steps",
+            "l2": "flushed between timed steps (512 MiB write)" if flush else "inputs larger than L2",
+            "seed": scene.seed, "dt_ns": scene.dt[1],
+            "mean_neighbours": st.neighbour_total / max(n, 1), "candidates_per_agent": st.candidate_total / max(n, 1),
+            "finite_tti_fraction": st.finite_tti_count / max(n, 1), "nonfinite": int(st.nonfinite_count),
+            "oob": int(st.oob_count),
+        },
+        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+        "cpu_baseline": {"value": cpu_v, "unit": "agent-steps/s", "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores_available": os.cpu_count()},
+        "clocks": clk, "wall_s_timed_region": wall1 - wall0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def fp64_info(args):
+    import ctypes as C
+
+    from rmf_crowdsim_b200 import _native as N
+
+    try:
+        a, b = C.c_double(), C.c_double()
+        if N.load().rcs_fp64_peak(0, C.byref(a), C.byref(b)) == 0:
+            return {"dfma_tflops": a.value, "dadd_tops": b.value}
+    except Exception:
+        pass
+    return None
+
+
+def run_e2e(scene, frozen: bool, steps: int, warmup: int) -> dict:
+    """Host-buffer path: rcs_set_preferred_velocity (H2D from pinned) + rcs_step_async + rcs_read_agents
+    (D2H to pinned), all inside the timed region."""
+    import ctypes as C
+
+    from rmf_crowdsim_b200 import Duration, _native as N
+    from rmf_crowdsim_b200 import sim as S
+
+    n = scene.n
+    lib = N.load()
+    idx = S.LocationHash2D(scene.width, scene.height, scene.cell, scene.offset, capacity=n, device=0)
+    sim = S.Simulation(idx)
+    h = sim._h
+
+    class HostPlan(S.HighLevelPlanner):  # evaluated by the caller, uploaded every step
+        pass
+
+    hl = HostPlan()
+    lp = S.NoLocalPlan() if scene.lp[0] == "none" else S.Zanlungo(*scene.lp[1:])
+    from rmf_crowdsim_b200.scenes import add_agents_bulk
+
+    add_agents_bulk(sim, scene.xy, hl, lp, scene.eyesight)
+    sim._host_hl.clear()  # the bulk path below replaces the per-agent Python callbacks
+    sim.set_state(None, vx=scene.vxy[:, 0].copy(), vy=scene.vxy[:, 1].copy())
+
+    def pinned(count, dtype):
+        p = C.c_void_p()
+        nbytes = count * np.dtype(dtype).itemsize
+        N.check(None, lib.rcs_host_alloc(nbytes, C.byref(p)))
+        buf = (C.c_char * nbytes).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=count), p
+
+    pref, pref_p = pinned(2 * n, np.float64)
+    outs = [pinned(n, np.float64) for _ in range(4)]
+    speed = scene.hl[1]
+    par = (np.arange(n) % 2 == 0)
+    pref[0::2] = np.where(par, -speed[0], speed[0])
+    pref[1::2] = np.where(par, -speed[1], speed[1])
+    dt = Duration(*scene.dt)
+    out_n = C.c_uint64()
+
+    def one():
+        N.check(h, lib.rcs_set_preferred_velocity(h, n, None, pref.ctypes.data_as(N.c_f64p)))
+        N.check(h, lib.rcs_step_async(h, dt.secs, dt.nanos, N.RCS_STEP_NO_COMMIT if frozen else 0))
+        N.check(h, lib.rcs_read_agents(h, N.RCS_ORDER_ID, n, None, *[o[0].ctypes.data_as(N.c_f64p) for o in outs],
+                                       None, C.byref(out_n)))
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    t1 = time.perf_counter()
+    res = {"value": n * steps / (t1 - t0), "unit": "agent-steps/s", "h2d_bytes_per_step": 16 * n,
+           "d2h_bytes_per_step": 32 * n, "steps": steps,
+           "path": "rcs_set_preferred_velocity(pinned host) + rcs_step_async + rcs_read_agents(ORDER_ID, pinned host)"}
+    for _, p in [(pref, pref_p)] + outs:
+        lib.rcs_host_free(p)
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--variant", default="shuffled", choices=["shuffled", "lane"])
+    ap.add_argument("--no-local-plan", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if args.gpus == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        run_gpu_single(args)
+    else:
+        from rmf_crowdsim_b200 import dist_bench
+
+        dist_bench.run(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,237 @@
+/* rcs.h -- C ABI of the B200-native per-timestep agent update of rmf_crowdsim.
+ *
+ * This is the drop-in boundary: the entry points below are what a Rust `-sys` crate for the
+ * reference (open-rmf/rmf_crowdsim) would bind in place of the reference's CPU hot path.  Plain
+ * pointers and sizes only; opaque handle; `int` status (0 = OK).  One handle is used by one
+ * thread at a time (the reference is single-threaded, lib.rs:69-91).  The caller owns every host
+ * buffer for the duration of the call only; the library owns all device memory.  The library never
+ * calls back into the host language: events are polled (rcs_poll_events).
+ *
+ * There is NO CPU fallback: every entry point that computes needs a CUDA device and fails with
+ * RCS_ERR_NO_DEVICE / RCS_ERR_CUDA otherwise.
+ *
+ * Reference file:line citations are relative to /root/reference/rmf_crowdsim/src.
+ *
+ * Index semantic: DEFERRED -- within one step every radius query sees the
+ * start-of-step positions of all agents (the reference mutates its index inside a HashMap-ordered
+ * loop, lib.rs:299, which makes its own results order-dependent and irreproducible).
+ */
+#ifndef RCS_H_
+#define RCS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RCS_ABI_VERSION 1
+
+typedef struct rcs_sim rcs_sim;
+
+/* Status codes.  rcs_last_error() returns the reference's literal message where one exists:
+ *   RCS_ERR_OUT_OF_BOUNDS -> "Index out of bounds"               (location_hash_2d.rs:62)
+ *   RCS_ERR_SPAWN         -> "Failed to add agents from source"  (lib.rs:252)               */
+enum {
+  RCS_OK = 0,
+  RCS_ERR_OUT_OF_BOUNDS = 1,
+  RCS_ERR_SPAWN = 2,
+  RCS_ERR_CUDA = 3,
+  RCS_ERR_NCCL = 4,
+  RCS_ERR_CAPACITY = 5,
+  RCS_ERR_ARG = 6,
+  RCS_ERR_NO_DEVICE = 7,
+  RCS_ERR_HALO = 8 /* multi-GPU: an agent moved further than the halo width in one step */
+};
+
+/* LocationHash2D::new(width, height, cell_size, offset)  (location_hash_2d.rs:33-51) plus the
+ * device placement.  n_x = (width/cell_size) as usize, n_y = (height/cell_size) as usize. */
+typedef struct rcs_sim_desc {
+  double width;
+  double height;
+  double cell_size;
+  double offset_x;
+  double offset_y;
+  uint64_t capacity; /* maximum number of live agents held by this handle (per rank) */
+  int32_t device;    /* CUDA device ordinal */
+  uint32_t flags;    /* reserved, 0 */
+} rcs_sim_desc;
+
+/* Per-step counters: non-finite values are NOT errors in the reference
+ * (a NaN position lands in cell 0 through the saturating cast), so they are only counted. */
+typedef struct rcs_stats {
+  uint64_t n_agents;          /* live agents after the step */
+  uint64_t oob_count;         /* agents whose new position failed location_to_index */
+  uint64_t first_oob_id;      /* smallest such id (UINT64_MAX if none) */
+  uint64_t nonfinite_count;   /* agents whose new position or velocity is not finite */
+  uint64_t finite_tti_count;  /* agents whose t_i was finite (ran the force pass) */
+  uint64_t neighbour_total;   /* sum over agents of neighbour-list lengths (after self filter) */
+  uint64_t candidate_total;   /* sum over agents of candidates distance-tested */
+  uint64_t spawned;           /* agents spawned by source sinks in this step */
+  uint64_t destroyed;         /* agents removed at sinks in this step */
+  uint64_t steps;             /* steps executed on this handle */
+} rcs_stats;
+
+uint32_t rcs_abi_version(void);
+
+/* Simulation::new(LocationHash2D::new(..))  (lib.rs:103-116) */
+int rcs_sim_create(const rcs_sim_desc* desc, rcs_sim** out);
+void rcs_sim_destroy(rcs_sim* sim);
+/* Message of the last failing call on this handle ("" if none); sim may be NULL for create errors. */
+const char* rcs_last_error(const rcs_sim* sim);
+
+/* ---- planner descriptors --------------------------------------------------------------------
+ * The reference passes planners as Arc<Mutex<dyn Trait>> per add_agents group (lib.rs:119-125).
+ * Here a group names device-side planner descriptors instead. */
+
+/* local_planners::no_local_plan::NoLocalPlan  (no_local_plan.rs:7-18) */
+int rcs_lp_none(rcs_sim* sim, uint32_t* out_lp);
+/* local_planners::zanlungo::Zanlungo::new, same argument order (zanlungo.rs:31-38) */
+int rcs_lp_zanlungo(rcs_sim* sim, double agent_scale, double obstacle_scale, double reaction_time,
+                    double force_distance, double agent_mass, double agent_radius, uint32_t* out_lp);
+
+/* HighLevelPlanner::get_desired_velocity (highlevel_planners.rs:9) evaluated on the device:
+ *  constant: Some(v) for every agent            (fixture of lib.rs:391-420)
+ *  parity  : even id -> Some(-v), odd -> Some(v) (fixture of rmf_crowdsim_viz/src/main.rs:20-30)
+ *  host    : Some(table[id]) as uploaded by rcs_set_preferred_velocity, None for ids never set
+ *            (slow path that keeps user-implemented HighLevelPlanner trait objects usable)
+ *  none    : always None  => velocity (0,0)     (lib.rs:263-273) */
+int rcs_hl_constant(rcs_sim* sim, double vx, double vy, uint32_t* out_hl);
+int rcs_hl_parity(rcs_sim* sim, double vx, double vy, uint32_t* out_hl);
+int rcs_hl_host(rcs_sim* sim, uint32_t* out_hl);
+int rcs_hl_none(rcs_sim* sim, uint32_t* out_hl);
+
+/* ---- agents ---------------------------------------------------------------------------------- */
+
+/* Simulation::add_agents (lib.rs:119-156).  xy = n interleaved (x,y).  Ids are allocated
+ * sequentially from last_alloc_agent_id (lib.rs:128-129) and written to out_ids (may be NULL).
+ * Velocity starts at (0,0), next_waypoint at 0.  Returns RCS_ERR_OUT_OF_BOUNDS if any position
+ * fails location_to_index; in that case NO agent of the call is added (the reference leaves the
+ * failing agent half-inserted, lib.rs:133-149 -- documented deviation). */
+int rcs_add_agents(rcs_sim* sim, uint64_t n, const double* xy, uint32_t hl, uint32_t lp, double eyesight,
+                   uint64_t* out_ids);
+/* Simulation::remove_agents (lib.rs:176-192), batched. Unknown ids -> RCS_ERR_ARG. */
+int rcs_remove_agents(rcs_sim* sim, uint64_t n, const uint64_t* ids);
+/* `agents` is a pub field (lib.rs:71): position and velocity are user-writable.  Takes effect
+ * immediately for the index too (snapshot injection).  ids == NULL means "all live agents in
+ * ascending-id order". */
+int rcs_set_state(rcs_sim* sim, uint64_t n, const uint64_t* ids, const double* x, const double* y,
+                  const double* vx, const double* vy);
+/* Upload Some(v) results of host-side HighLevelPlanner objects for agents of rcs_hl_host groups.
+ * vxy = n interleaved (vx,vy).  ids == NULL: all live agents in ascending-id order. */
+int rcs_set_preferred_velocity(rcs_sim* sim, uint64_t n, const uint64_t* ids, const double* vxy);
+
+#define RCS_ORDER_STORAGE 0u /* device storage order (cell-sorted after a step) */
+#define RCS_ORDER_ID 1u      /* ascending agent id */
+/* Read back the pub `agents` view (lib.rs:71).  Any output pointer may be NULL.  cap = capacity of
+ * the output arrays in agents; *out_n = number of live agents. */
+int rcs_read_agents(rcs_sim* sim, uint32_t order, uint64_t cap, uint64_t* ids, double* x, double* y, double* vx,
+                    double* vy, uint32_t* next_waypoint, uint64_t* out_n);
+int rcs_agent_count(rcs_sim* sim, uint64_t* out_n);
+
+/* ---- the hot path ---------------------------------------------------------------------------- */
+
+#define RCS_STEP_DEFAULT 0u
+/* Run the whole pipeline but do not commit (state stays the pre-step snapshot).  Used to time the
+ * force kernel on crowds that the reference model itself drives non-finite within a few steps
+ * (SURVEY.md section 0.4 / 8d "frozen-snapshot mode"). */
+#define RCS_STEP_NO_COMMIT 1u
+
+/* Simulation::step(Duration::new(secs, nanos))  (lib.rs:195-383): spawn phase, per-agent update
+ * (high-level velocity -> radius query -> local planner -> explicit Euler), commit, removals.
+ * dt = secs as f64 + nanos as f64 / 1e9, bit-identical to Duration::as_secs_f64.
+ * Synchronous.  On RCS_ERR_OUT_OF_BOUNDS the step is NOT committed (the reference aborts mid-loop
+ * with a half-updated index, lib.rs:299-302 -- documented deviation). */
+int rcs_step(rcs_sim* sim, uint64_t secs, uint32_t nanos);
+/* Enqueue one step without waiting; errors become sticky and are returned by rcs_sync.  A step
+ * enqueued after a failed one is skipped on the device. */
+int rcs_step_async(rcs_sim* sim, uint64_t secs, uint32_t nanos, uint32_t flags);
+int rcs_sync(rcs_sim* sim);
+int rcs_step_stats(rcs_sim* sim, rcs_stats* out);
+
+/* Events for EventListener::{agent_spawned, agent_destroyed} (lib.rs:22-33), accumulated since the
+ * last poll, each list in ascending id order per step.  Any pointer may be NULL; counts are always
+ * written. */
+int rcs_poll_events(rcs_sim* sim, uint64_t spawned_cap, uint64_t* spawned_ids, double* spawned_xy,
+                    uint64_t* n_spawned, uint64_t destroyed_cap, uint64_t* destroyed_ids, uint64_t* n_destroyed);
+
+/* ---- source sinks (lib.rs:159-168, 199-254, 305-336; source_sink.rs:36-100) -------------------- */
+typedef struct rcs_source_sink_desc {
+  double source_x, source_y;
+  double radius_sink;
+  double monotonic_rate; /* MonotonicCrowd::new(rate): round(dt*rate) per step (source_sink.rs:96-100) */
+  uint32_t hl, lp;
+  uint64_t n_waypoints;
+  const double* waypoints_xy; /* interleaved; the last waypoint is the sink */
+  int32_t loop_forever;
+  double agent_eyesight_range;
+} rcs_source_sink_desc;
+int rcs_add_source_sink(rcs_sim* sim, const rcs_source_sink_desc* desc, uint64_t* out_id);
+int rcs_remove_source_sink(rcs_sim* sim, uint64_t id);
+
+/* ---- SpatialIndex trait, batched (spatial_index.rs:4-14) ------------------------------------- */
+
+/* LocationHash2D::location_to_index for n points (location_hash_2d.rs:54-66): data index or -1. */
+int rcs_cell_of(rcs_sim* sim, uint64_t n, const double* xy, int64_t* out_idx);
+/* SpatialIndex::add_or_update / remove_agent with caller-chosen ids (location_hash_2d.rs:126-149,
+ * 260-267), for using the handle as a bare GpuLocationHash2D.  Ids must be < 2^31. */
+int rcs_index_add_or_update(rcs_sim* sim, uint64_t n, const uint64_t* ids, const double* xy);
+int rcs_index_remove(rcs_sim* sim, uint64_t n, const uint64_t* ids);
+/* SpatialIndex::get_neighbours_in_radius for nq queries (location_hash_2d.rs:240-258), CSR output:
+ * ids of query q are out_ids[offsets[q] .. offsets[q+1]) in canonical order (cells x-major then y,
+ * ascending id inside a cell; the reference's order inside a cell is HashSet-random).  If the total
+ * exceeds ids_cap, returns RCS_ERR_CAPACITY with offsets filled (offsets[nq] = required size). */
+int rcs_query_radius(rcs_sim* sim, uint64_t nq, const double* qxy, const double* radius, uint64_t* offsets,
+                     uint64_t* out_ids, uint64_t ids_cap);
+/* SpatialIndex::get_nearest_neighbours for nq queries (location_hash_2d.rs:151-238), including its
+ * ring-search quirks; out_ids has nq*k slots, out_counts[q] <= k valid entries per query. */
+int rcs_query_knn(rcs_sim* sim, uint64_t nq, const double* qxy, uint64_t k, uint64_t* out_ids,
+                  uint64_t* out_counts);
+
+/* ---- parity trace -----------------------------------------------------------------------------
+ * With tracing on, each step also records per agent: t_i (zanlungo.rs:76-91), the summed force
+ * (zanlungo.rs:210-215), and the neighbour list handed to the local planner (lib.rs:281-286). */
+int rcs_set_trace(rcs_sim* sim, int32_t on);
+int rcs_trace_sizes(rcs_sim* sim, uint64_t* n_agents, uint64_t* n_neighbours);
+/* Ascending-id order; nb_offsets has n_agents+1 entries. */
+int rcs_read_trace(rcs_sim* sim, uint64_t* ids, double* t_i, double* fx, double* fy, uint64_t* nb_offsets,
+                   uint64_t* nb_ids);
+
+/* ---- measurement helpers ---------------------------------------------------------------------- */
+#define RCS_NUM_EVENTS 64u
+int rcs_event_record(rcs_sim* sim, uint32_t slot);
+int rcs_event_elapsed_ms(rcs_sim* sim, uint32_t start_slot, uint32_t stop_slot, float* out_ms);
+/* Pinned host memory so that host<->device copies of caller buffers run at full PCIe rate. */
+int rcs_host_alloc(uint64_t bytes, void** out);
+int rcs_host_free(void* p);
+/* Write a device buffer of `bytes` (> L2) on the handle's stream to evict L2 between timed steps. */
+int rcs_flush_l2(rcs_sim* sim, uint64_t bytes);
+/* Bracket the dominant kernel (step_kernel) of every step with CUDA events on the launching stream;
+ * rcs_kernel_time_ms returns the accumulated device time and the number of launches since timing
+ * was switched on (it waits for the stream). */
+int rcs_kernel_timing(rcs_sim* sim, int32_t on);
+int rcs_kernel_time_ms(rcs_sim* sim, double* out_ms, uint64_t* out_launches);
+/* Number of kernels launched by this handle so far. */
+int rcs_launch_count(rcs_sim* sim, uint64_t* out);
+/* FP64 pipe peak microbenchmark (dependent DFMA chains on all SMs); out_tflops counts FMA = 2. */
+int rcs_fp64_peak(int32_t device, double* out_tflops, double* out_dadd_tops);
+
+/* ---- multi-GPU spatial strips ------------------------------------------
+ * One process per GPU.  Strips are whole cell columns in x (the cell index is x-major,
+ * location_hash_2d.rs:59).  rcs_nccl_unique_id is called on rank 0 and the 128 bytes are
+ * distributed by the host program (e.g. torch.distributed); rcs_dist_init then builds the NCCL
+ * communicator inside the library.  Agents are handed to the rank that owns their column with
+ * rcs_add_agents as usual (each rank adds only its own; ids are supplied by rcs_dist_add_agents). */
+int rcs_nccl_unique_id(uint8_t out_id[128]);
+int rcs_dist_init(rcs_sim* sim, int32_t rank, int32_t world, const uint8_t nccl_id[128]);
+/* Column range [c0, c1) owned by `rank` of `world` for this handle's grid. */
+int rcs_dist_strip(rcs_sim* sim, int32_t rank, int32_t world, uint64_t* c0, uint64_t* c1);
+/* add_agents with caller-supplied global ids (the global sequential allocation of lib.rs:128-129
+ * is done by the host program across ranks). */
+int rcs_dist_add_agents(rcs_sim* sim, uint64_t n, const uint64_t* ids, const double* xy, const double* vxy,
+                        uint32_t hl, uint32_t lp, double eyesight);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RCS_H_ */
