@@ -83,3 +83,10 @@ def step_both(g, o, scene: SC.Scene):
 
     g.step(Duration(*scene.dt))
     o.step(*scene.dt)
+
+
+def resync(g, o) -> None:
+    """Make the CUDA simulation's state bit-identical to the oracle's (ascending-id arrays)."""
+    so = o.read_state()
+    if len(so["id"]):
+        g.set_state(None, so["x"], so["y"], so["vx"], so["vy"])

@@ -12,13 +12,19 @@ from rmf_crowdsim_b200 import scenes as SC
 pytestmark = pytest.mark.gpu
 
 
-def _run(scene, steps, trace=True):
+def _run(scene, steps, trace=True, resync=True):
+    """Per-step parity on IDENTICAL inputs: before every step the oracle's state is injected into the
+    CUDA simulation (CUDA's exp/asin/sin differ from glibc's in the last ulp, so free-running
+    trajectories separate at the 1e-16 level after the first interaction; that drift is reported by
+    test_gpu_drift.py, not asserted bit-exact here)."""
     g = SC.build_simulation(scene)
     o = P.build_oracle(scene)
     g.set_trace(trace)
     o.enable_trace(trace)
     worst = {"force_rel_err": 0.0, "vel_rel_err": 0.0, "pos_rel_err": 0.0, "finite_tti": 0}
     for _ in range(steps):
+        if resync:
+            P.resync(g, o)
         P.step_both(g, o, scene)
         if trace:
             r = P.compare_traces(g.read_trace(), o.read_trace())
@@ -102,6 +108,7 @@ def test_wide_stencil_and_mixed_groups():
     g.set_trace(True)
     o.enable_trace(True)
     for _ in range(2):
+        P.resync(g, o)
         g.step(R.Duration(0, 10_000_000))
         o.step(0, 10_000_000)
         tg, to = g.read_trace(), o.read_trace()
@@ -141,6 +148,7 @@ def test_host_planner_slow_path_matches_oracle_table_planner():
     hl = o.hl_host()
     o.add_agents(xy, hl, o.lp_zanlungo(*z), 2.0)
     for _ in range(3):
+        P.resync(g, o)
         so = o.read_state()
         sel = so["id"] % 5 != 0
         vxy = np.stack([-0.1 * so["y"][sel], 0.1 * so["x"][sel]], axis=1)
@@ -160,6 +168,7 @@ def test_remove_agents_then_step():
         o.remove_agent(i)
     assert g.agent_count() == o.agent_count() == 251
     for _ in range(2):
+        P.resync(g, o)
         P.step_both(g, o, scene)
         s = P.compare_states(g.read_state(), o.read_state())
         assert s["vel_rel_err"] <= P.REL_TOL and s["pos_rel_err"] <= P.REL_TOL
