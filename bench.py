@@ -204,6 +204,8 @@ def run_gpu_single(args):
     dt = Duration(*scene.dt)
     sim = SC.build_simulation(scene, device=0)
     lib, h = sim._lib, sim._h
+    if args.kernel:
+        sim.set_option(N.RCS_OPT_STEP_KERNEL, args.kernel)
     n = scene.n
     state_bytes = n * 48 * 2
     flush = state_bytes < (1 << 30)
@@ -254,7 +256,7 @@ def run_gpu_single(args):
 
     # end to end through the C ABI with HOST buffers: every step uploads the preferred velocities of a host
     # HighLevelPlanner (pinned), runs the step, and reads back x,y,vx,vy of every agent (pinned).
-    e2e = run_e2e(scene, frozen, min(K, 10), max(3, min(args.warmup, 5)))
+    e2e = None if args.skip_e2e else run_e2e(scene, frozen, min(K, 10), max(3, min(args.warmup, 5)))
     clk = clocks.stop()
 
     peaks, how = measured_peaks()
@@ -283,7 +285,7 @@ def run_gpu_single(args):
     sample_scene, sample = cpu_sample_scene(workload, args.variant, 6)
     if args.no_local_plan:
         sample_scene.lp = ("none",)
-    cpu_v, _ = oracle_run(sample_scene, 5, 1)
+    cpu_v = None if args.skip_cpu else oracle_run(sample_scene, 5, 1)[0]
     line = {
         "metric": "agent-steps/sec (query+Zanlungo+integrate)", "value": value, "unit": "agent-steps/s",
         "n_gpus": 1, "steps": K, "warmup": args.warmup, "ms_per_step": total_ms / K, "higher_is_better": True,
@@ -389,6 +391,9 @@ def main():
     ap.add_argument("--workload", default=None)
     ap.add_argument("--variant", default="shuffled", choices=["shuffled", "lane"])
     ap.add_argument("--no-local-plan", action="store_true")
+    ap.add_argument("--kernel", type=int, default=0, help="RCS_OPT_STEP_KERNEL: 0 default, 1 thread/agent, 2 warp")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -197,6 +197,10 @@ int rcs_trace_sizes(rcs_sim* sim, uint64_t* n_agents, uint64_t* n_neighbours);
 int rcs_read_trace(rcs_sim* sim, uint64_t* ids, double* t_i, double* fx, double* fy, uint64_t* nb_offsets,
                    uint64_t* nb_ids);
 
+/* ---- options ------------------------------------------------------------------------------------ */
+#define RCS_OPT_STEP_KERNEL 1u /* 0 = default (warp-cooperative), 1 = thread-per-agent, 2 = warp-cooperative */
+int rcs_set_option(rcs_sim* sim, uint32_t option, uint64_t value);
+
 /* ---- measurement helpers ---------------------------------------------------------------------- */
 #define RCS_NUM_EVENTS 64u
 int rcs_event_record(rcs_sim* sim, uint32_t slot);

@@ -32,6 +32,7 @@ RCS_ORDER_ID = 1
 RCS_STEP_DEFAULT = 0
 RCS_STEP_NO_COMMIT = 1
 RCS_NUM_EVENTS = 64
+RCS_OPT_STEP_KERNEL = 1
 
 
 class SimDesc(C.Structure):
@@ -116,6 +117,7 @@ SIGNATURES = {
     "rcs_set_trace": (C.c_int, [C.c_void_p, C.c_int32]),
     "rcs_trace_sizes": (C.c_int, [C.c_void_p, c_u64p, c_u64p]),
     "rcs_read_trace": (C.c_int, [C.c_void_p, c_u64p, c_f64p, c_f64p, c_f64p, c_u64p, c_u64p]),
+    "rcs_set_option": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64]),
     "rcs_event_record": (C.c_int, [C.c_void_p, C.c_uint32]),
     "rcs_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, c_f32p]),
     "rcs_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(C.c_void_p)]),

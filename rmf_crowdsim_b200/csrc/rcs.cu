@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "rcs_kernels.cuh"
+#include "rcs_step_warp.cuh"
 
 using namespace rcs;
 
@@ -97,6 +98,7 @@ struct rcs_sim {
   uint64_t launches = 0;
   rcs_stats stats{};
   cudaEvent_t events[RCS_NUM_EVENTS]{};
+  uint32_t opt_step_kernel = 0;
   // dominant-kernel timing
   bool ktiming = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kevents;  // pending pairs
@@ -339,14 +341,17 @@ cudaEvent_t kevent_get(rcs_sim* s) {
 }
 
 // launch the dominant kernel, optionally bracketed by events on the launching stream
-void launch_step_kernel(rcs_sim* s, const StepArgs& a, uint32_t n) {
+void launch_step_kernel(rcs_sim* s, const StepArgs& a, uint32_t n, bool sorted_input = true) {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (s->ktiming) {
     e0 = kevent_get(s);
     e1 = kevent_get(s);
     cudaEventRecord(e0, s->stream);
   }
-  step_kernel<<<blocks_for(n, 128), 128, 0, s->stream>>>(a);
+  if (sorted_input && s->opt_step_kernel != 1)
+    step_warp_kernel<<<blocks_for(n, 32 * SW_WARPS), 32 * SW_WARPS, 0, s->stream>>>(a);
+  else
+    step_kernel<<<blocks_for(n, 128), 128, 0, s->stream>>>(a);
   s->launches += 1;
   if (s->ktiming) {
     cudaEventRecord(e1, s->stream);
@@ -953,7 +958,7 @@ int rcs_step_async(rcs_sim* s, uint64_t secs, uint32_t nanos, uint32_t flags) {
       // step is a pure stream over the agents in storage order; new x,y,vx,vy go to the spare buffers.
       StepArgs a = make_step_args(s, s->cur, s->srt, dt);
       a.n_sorted = s->scan_total + 1;  // constant 0xffffffff: every slot below n is live in storage order
-      launch_step_kernel(s, a, n);
+      launch_step_kernel(s, a, n, false);
       p.snapshot_in_srt = false;
       if (!no_commit) {
         std::swap(s->cur.x, s->srt.x);
@@ -1266,6 +1271,16 @@ int rcs_read_trace(rcs_sim* s, uint64_t* ids, double* t_i, double* fx, double* f
   }
   if (nb_offsets) nb_offsets[n] = off;
   return RCS_OK;
+}
+
+int rcs_set_option(rcs_sim* s, uint32_t option, uint64_t value) {
+  if (!s) return RCS_ERR_ARG;
+  if (option == RCS_OPT_STEP_KERNEL && value <= 2) {
+    s->opt_step_kernel = (uint32_t)value;
+    return RCS_OK;
+  }
+  s->err = "unknown option or value";
+  return RCS_ERR_ARG;
 }
 
 int rcs_event_record(rcs_sim* s, uint32_t slot) {

@@ -497,6 +497,9 @@ class Simulation:
                                                   _p(fy, N.c_f64p), _p(off, N.c_u64p), _p(nb, N.c_u64p)))
         return {"id": ids, "t_i": ti, "fx": fx, "fy": fy, "nb_offsets": off, "nb_ids": nb[: nn.value]}
 
+    def set_option(self, option: int, value: int) -> None:
+        N.check(self._h, self._lib.rcs_set_option(self._h, int(option), int(value)))
+
     def stats(self) -> N.Stats:
         st = N.Stats()
         N.check(self._h, self._lib.rcs_step_stats(self._h, C.byref(st)))
