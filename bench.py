@@ -200,7 +200,9 @@ def run_gpu_single(args):
 
     workload = args.workload or "c3"
     scene = make_scene(workload, args.variant, lp_none=args.no_local_plan)
-    frozen = args.variant == "shuffled" and not args.no_local_plan
+    # committed steps only for the lane-ordered Zanlungo crowd (stays finite); everything else is timed on a
+    # frozen snapshot so that agents cannot walk out of the hash domain during a long run
+    frozen = not (args.variant == "lane" and not args.no_local_plan)
     dt = Duration(*scene.dt)
     sim = SC.build_simulation(scene, device=0)
     lib, h = sim._lib, sim._h
@@ -220,9 +222,11 @@ def run_gpu_single(args):
     sim.sync()
     clocks.start()
     t_end = time.time() + 0.4
-    while time.time() < t_end:
+    heat = 0
+    while time.time() < t_end and heat < 600:  # 600 committed steps = 13 m of the 64 m margin
         for _ in range(8):
             one_step()
+        heat += 8
         sim.sync()
 
     # timed region: K steps, each bracketed by events on the launching stream, L2 flushed in between

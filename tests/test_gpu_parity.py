@@ -92,15 +92,18 @@ def test_wide_stencil_and_mixed_groups():
     off = (-5.0, -5.0)
     o = O.OracleSim(w, h, 1.0, off)
     g = R.Simulation(R.LocationHash2D(w, h, 1.0, off, capacity=4096))
-    xy_a = rng.uniform(-6.0, 30.0, size=(600, 2))
-    xy_b = rng.uniform(0.0, 25.0, size=(300, 2))
+    # jittered lattices (no pair inside agent_radius: the model turns overlaps into 1e15 forces)
+    lat = SC.jittered_lattice(30, 30, 1.2, 21) - 7.0          # spans [-7, 29]: some agents left of / below the origin
+    sel = rng.permutation(900)
+    xy_a = lat[sel[:600]]
+    xy_b = lat[sel[600:]] + 0.37
     za = (0.3, 1.0, 0.0, 0.7, 1.5, 0.25)
     oa = o.add_agents(xy_a, o.hl_parity((0.8, 0.3)), o.lp_zanlungo(*za), 4.5)
     ob = o.add_agents(xy_b, o.hl_constant((0.1, -0.4)), o.lp_none(), 2.0)
     ga = g.add_agents(xy_a, R.ParityVelocityPlan((0.8, 0.3)), R.Zanlungo(*za), 4.5)
     gb = g.add_agents(xy_b, R.ConstantVelocityPlan((0.1, -0.4)), R.NoLocalPlan(), 2.0)
     assert list(oa) == ga and list(ob) == gb
-    v = rng.uniform(-1, 1, size=(900, 2))
+    v = rng.uniform(-0.5, 0.5, size=(900, 2))
     ids = np.arange(900, dtype=np.uint64)
     allxy = np.concatenate([xy_a, xy_b])
     o.set_state(ids, allxy[:, 0], allxy[:, 1], v[:, 0], v[:, 1])
@@ -122,13 +125,40 @@ def test_wide_stencil_and_mixed_groups():
 
 
 def test_crowded_cells_use_the_block_sorter():
-    """> 32 agents in one cell exercises sort_big_cells_kernel; order must still be canonical."""
+    """> 32 agents in one cell exercises sort_big_cells_kernel; order must still be canonical.
+    15 x 15 agents at 0.25 m spacing in 2 x 2 cells of 2 m; agent_radius 0.05 so nobody overlaps."""
     rng = np.random.default_rng(5)
-    scene = SC.uniform_crowd(8, "shuffled", margin=8.0, seed=2)
-    scene.xy = rng.uniform(0.0, 3.9, size=(200, 2))  # 200 agents in 2 x 2 cells of 2 m
-    scene.vxy = rng.uniform(-1, 1, size=(200, 2))
+    scene = SC.uniform_crowd(15, "shuffled", s=0.25, margin=8.0, seed=2,
+                             lp=("zanlungo", 0.01, 1.0, 0.0, 0.5, 1.0, 0.05))
+    scene.vxy = rng.uniform(-0.2, 0.2, size=(225, 2))
     worst, g, o = _run(scene, 2)
+    assert worst["finite_tti"] > 0
     assert worst["force_rel_err"] <= P.REL_TOL and worst["vel_rel_err"] <= P.REL_TOL
+
+
+def test_overlapping_agents_fail_identically():
+    """Two agents inside each other's agent_radius: t_i = 0 => 1e15-magnitude force for the lower id
+    (zanlungo.rs:64-66,165-167) => new position far outside the grid => Err("Index out of bounds")
+    from both implementations, and the CUDA state stays the pre-step snapshot."""
+    z = (0.05, 1.0, 0.0, 0.5, 1.0, 0.2)
+    xy = np.array([[5.0, 5.0], [5.1, 5.0], [8.0, 8.0]])
+    g = R.Simulation(R.LocationHash2D(16, 16, 2.0, (0.0, 0.0), capacity=8))
+    g.add_agents(xy, R.ParityVelocityPlan((1.0, 0.0)), R.Zanlungo(*z), 2.0)
+    o = O.OracleSim(16, 16, 2.0, (0.0, 0.0))
+    o.add_agents(xy, o.hl_parity((1.0, 0.0)), o.lp_zanlungo(*z), 2.0)
+    # first step: velocities are 0 => a = 0 => t_i = inf (SURVEY.md section 9); second step interacts
+    g.step(R.Duration(0, 1_000_000))
+    o.step(0, 1_000_000)
+    before = g.read_state()
+    with pytest.raises(O.OracleError) as eo:
+        o.step(0, 16_666_667)
+    with pytest.raises(R.CrowdsimError) as eg:
+        g.step(R.Duration(0, 16_666_667))
+    assert str(eo.value) == str(eg.value) == "Index out of bounds"
+    after = g.read_state()
+    for k in ("x", "y", "vx", "vy"):
+        assert np.array_equal(before[k].view(np.uint64), after[k].view(np.uint64))
+    assert g.stats().first_oob_id == 0
 
 
 def test_host_planner_slow_path_matches_oracle_table_planner():
@@ -140,7 +170,7 @@ def test_host_planner_slow_path_matches_oracle_table_planner():
             return (-0.1 * y, 0.1 * x)
 
     rng = np.random.default_rng(3)
-    xy = rng.uniform(2.0, 18.0, size=(300, 2))
+    xy = SC.jittered_lattice(18, 18, 0.9, 8)[rng.permutation(324)[:300]] + 2.0
     z = (0.05, 1.0, 0.0, 0.5, 1.0, 0.2)
     g = R.Simulation(R.LocationHash2D(24, 24, 2.0, (-2.0, -2.0), capacity=512))
     g.add_agents(xy, Swirl(), R.Zanlungo(*z), 2.0)
