@@ -136,29 +136,47 @@ def test_crowded_cells_use_the_block_sorter():
     assert worst["force_rel_err"] <= P.REL_TOL and worst["vel_rel_err"] <= P.REL_TOL
 
 
-def test_overlapping_agents_fail_identically():
-    """Two agents inside each other's agent_radius: t_i = 0 => 1e15-magnitude force for the lower id
-    (zanlungo.rs:64-66,165-167) => new position far outside the grid => Err("Index out of bounds")
-    from both implementations, and the CUDA state stays the pre-step snapshot."""
+@pytest.mark.parametrize("lower_id_on_the_right", [True, False])
+def test_overlapping_agents_behave_identically(lower_id_on_the_right):
+    """Two agents inside each other's agent_radius: t_i = 0 => 1e15-magnitude tangential force for the
+    lower id (zanlungo.rs:64-66,165-167).  Pushed towards +y the new position fails location_to_index
+    => Err("Index out of bounds") from both implementations and the CUDA state stays the pre-step
+    snapshot; pushed towards -y the saturating cast (location_hash_2d.rs:57) files the agent in row 0
+    and NO error is raised -- by either implementation."""
     z = (0.05, 1.0, 0.0, 0.5, 1.0, 0.2)
-    xy = np.array([[5.0, 5.0], [5.1, 5.0], [8.0, 8.0]])
+    xy = np.array([[5.1, 5.0], [5.0, 5.0], [8.0, 8.0]]) if lower_id_on_the_right else \
+        np.array([[5.0, 5.0], [5.1, 5.0], [8.0, 8.0]])
     g = R.Simulation(R.LocationHash2D(16, 16, 2.0, (0.0, 0.0), capacity=8))
     g.add_agents(xy, R.ParityVelocityPlan((1.0, 0.0)), R.Zanlungo(*z), 2.0)
     o = O.OracleSim(16, 16, 2.0, (0.0, 0.0))
     o.add_agents(xy, o.hl_parity((1.0, 0.0)), o.lp_zanlungo(*z), 2.0)
-    # first step: velocities are 0 => a = 0 => t_i = inf (SURVEY.md section 9); second step interacts
+    # first step: velocities are 0 => a = 0 => t_i = inf (SURVEY.md section 9); the second step interacts
     g.step(R.Duration(0, 1_000_000))
     o.step(0, 1_000_000)
+    P.resync(g, o)
     before = g.read_state()
-    with pytest.raises(O.OracleError) as eo:
+    err_o = err_g = None
+    try:
         o.step(0, 16_666_667)
-    with pytest.raises(R.CrowdsimError) as eg:
+    except O.OracleError as e:
+        err_o = str(e)
+    try:
         g.step(R.Duration(0, 16_666_667))
-    assert str(eo.value) == str(eg.value) == "Index out of bounds"
+    except R.CrowdsimError as e:
+        err_g = str(e)
+    assert err_o == err_g
     after = g.read_state()
-    for k in ("x", "y", "vx", "vy"):
-        assert np.array_equal(before[k].view(np.uint64), after[k].view(np.uint64))
-    assert g.stats().first_oob_id == 0
+    if err_o is not None:
+        assert err_o == "Index out of bounds"
+        for k in ("x", "y", "vx", "vy"):
+            assert np.array_equal(before[k].view(np.uint64), after[k].view(np.uint64))
+        assert g.stats().first_oob_id == 0
+    else:
+        so = o.read_state()
+        assert abs(so["vy"][0]) > 1e14  # the 1e15 cap was hit
+        s = P.compare_states(after, so)
+        assert s["vel_rel_err"] <= P.REL_TOL and s["pos_rel_err"] <= P.REL_TOL
+        assert g.spatial_index.cell_of(np.stack([after["x"], after["y"]], axis=1))[0] >= 0
 
 
 def test_host_planner_slow_path_matches_oracle_table_planner():
