@@ -331,6 +331,125 @@ __device__ __forceinline__ uint32_t for_each_neighbour(const GridDev& g, const u
   return cand;
 }
 
+// Zanlungo::get_desired_velocity (zanlungo.rs:201-218) for ONE agent, sequentially, in canonical
+// neighbour order: t_i (compute_tti) then the force sum.  The reference form of the hot path; the
+// warp-cooperative kernel must reproduce its results bit for bit and uses it for agents whose
+// stencil does not fit its fast path.
+__device__ __noinline__ void zanlungo_sequential(const StepArgs& a, uint32_t i, const Self& me, const GroupDev& g,
+                                                 double& t_i, double& fx, double& fy, uint32_t& nbc,
+                                                 uint32_t& cand) {
+  const double* __restrict__ xs = a.in.x;
+  const double* __restrict__ ys = a.in.y;
+  const double* __restrict__ vxs = a.in.vx;
+  const double* __restrict__ vys = a.in.vy;
+  const uint64_t* __restrict__ ids = a.in.id;
+  const double rr = g.rr;
+  t_i = RCS_INF;
+  fx = 0.0;
+  fy = 0.0;
+  // Zanlungo::compute_tti, zanlungo.rs:76-91
+  cand = for_each_neighbour(a.grid, a.cell_start, xs, ys, ids, me.px, me.py, me.id, g.eyesight, g.thr2,
+                            [&](uint32_t j, double dx, double dy, double d2) {
+                              nbc++;
+                              double col_time = time_to_collision(vxs[j] - me.vx, vys[j] - me.vy, dx, dy, d2, rr);
+                              if (col_time < t_i) t_i = col_time;
+                            });
+  // zanlungo.rs:210-215
+  if (t_i != RCS_INF) {
+    const OwnerPre pre = owner_precompute(me.px, me.py, me.vx, me.vy, me.pfx, me.pfy, t_i, g);
+    const double ti = t_i;
+    for_each_neighbour(a.grid, a.cell_start, xs, ys, ids, me.px, me.py, me.id, g.eyesight, g.thr2,
+                       [&](uint32_t j, double, double, double) {
+                         double qx, qy;
+                         if (pair_force_dispatch(pre, me.px, me.py, me.vx, me.vy, me.pfx, me.pfy, me.id, xs[j], ys[j],
+                                                 vxs[j], vys[j], ids[j], ti, g, qx, qy)) {
+                           fx = fx + qx;
+                           fy = fy + qy;
+                         }
+                       });
+  }
+}
+
+// HighLevelPlanner::get_desired_velocity on the device (lib.rs:263-273): returns the recommended
+// velocity and sets me.pfx/pfy (the clone's preferred_vel, lib.rs:271).
+__device__ __forceinline__ void high_level_velocity(const StepArgs& a, uint32_t i, const GroupDev& g, Self& me,
+                                                    double& velx, double& vely) {
+  velx = 0.0;
+  vely = 0.0;
+  me.pfx = 0.0;
+  me.pfy = 0.0;
+  switch (g.hl_kind) {
+    case HL_CONSTANT:
+      velx = g.hl_vx;
+      vely = g.hl_vy;
+      me.pfx = velx;
+      me.pfy = vely;
+      break;
+    case HL_PARITY:
+      if ((me.id & 1ull) == 0ull) {
+        velx = -g.hl_vx;
+        vely = -g.hl_vy;
+      } else {
+        velx = g.hl_vx;
+        vely = g.hl_vy;
+      }
+      me.pfx = velx;
+      me.pfy = vely;
+      break;
+    case HL_HOST: {
+      double hx = a.in.pvx[i], hy = a.in.pvy[i];
+      if (hx == hx) {  // NaN in x encodes None
+        velx = hx;
+        vely = hy;
+        me.pfx = hx;
+        me.pfy = hy;
+      }
+    } break;
+    default:
+      break;
+  }
+}
+
+// Explicit Euler + commit outputs + error accounting (lib.rs:295-302) for one agent.
+__device__ __forceinline__ void integrate_and_store(const StepArgs& a, uint32_t i, const Self& me, double velx,
+                                                    double vely, double t_i, double fx, double fy, uint32_t nbc) {
+  const double nx = me.px + velx * a.dt;
+  const double ny = me.py + vely * a.dt;
+  a.ox[i] = nx;
+  a.oy[i] = ny;
+  a.ovx[i] = velx;
+  a.ovy[i] = vely;
+  if (a.t_i) {
+    a.t_i[i] = t_i;
+    a.fx[i] = fx;
+    a.fy[i] = fy;
+    a.nb_count[i] = nbc;
+  }
+  uint64_t idx;
+  if (!location_to_index(a.grid, nx, ny, idx)) {  // add_or_update(new_pos) error path, lib.rs:299-302
+    atomicAdd(&a.status->oob_count, 1u);
+    atomicMin(&a.status->first_oob_id, (unsigned long long)me.id);
+  }
+  if (!(isfinite(nx) && isfinite(ny) && isfinite(velx) && isfinite(vely))) atomicAdd(&a.status->nonfinite_count, 1u);
+}
+
+__device__ __forceinline__ void warp_stats(const StepArgs& a, uint32_t cand, uint32_t nbc, uint32_t finite) {
+  if (!a.collect_stats) return;
+  unsigned long long c = cand, nb = nbc, ft = finite;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    c += __shfl_down_sync(0xffffffffu, c, d);
+    nb += __shfl_down_sync(0xffffffffu, nb, d);
+    ft += __shfl_down_sync(0xffffffffu, ft, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (c) atomicAdd(&a.status->candidate_total, c);
+    if (nb) atomicAdd(&a.status->neighbour_total, nb);
+    if (ft) atomicAdd(&a.status->finite_tti, ft);
+  }
+}
+
+// Thread-per-agent form of the hot kernel (also the streaming kernel of NoLocalPlan-only crowds).
 __global__ void __launch_bounds__(128) step_kernel(StepArgs a) {
   if (a.status->failed) return;
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -344,123 +463,19 @@ __global__ void __launch_bounds__(128) step_kernel(StepArgs a) {
     me.vx = a.in.vx[i];
     me.vy = a.in.vy[i];
     me.id = a.in.id[i];
-
-    // high-level planner, lib.rs:263-273
-    double velx = 0.0, vely = 0.0;
-    me.pfx = 0.0;
-    me.pfy = 0.0;
-    switch (g.hl_kind) {
-      case HL_CONSTANT:
-        velx = g.hl_vx;
-        vely = g.hl_vy;
-        me.pfx = velx;
-        me.pfy = vely;
-        break;
-      case HL_PARITY:
-        if ((me.id & 1ull) == 0ull) {
-          velx = -g.hl_vx;
-          vely = -g.hl_vy;
-        } else {
-          velx = g.hl_vx;
-          vely = g.hl_vy;
-        }
-        me.pfx = velx;
-        me.pfy = vely;
-        break;
-      case HL_HOST: {
-        double hx = a.in.pvx[i], hy = a.in.pvy[i];
-        if (hx == hx) {  // NaN in x encodes None
-          velx = hx;
-          vely = hy;
-          me.pfx = hx;
-          me.pfy = hy;
-        }
-      } break;
-      default:
-        break;
-    }
-
+    double velx, vely;
+    high_level_velocity(a, i, g, me, velx, vely);
     double t_i = RCS_INF, fx = 0.0, fy = 0.0;
     if (g.lp_kind == LP_ZANLUNGO) {
-      // Zanlungo::compute_tti, zanlungo.rs:76-91
-      const double* __restrict__ xs = a.in.x;
-      const double* __restrict__ ys = a.in.y;
-      const double* __restrict__ vxs = a.in.vx;
-      const double* __restrict__ vys = a.in.vy;
-      const uint64_t* __restrict__ ids = a.in.id;
-      const double rr = g.rr;
-      cand = for_each_neighbour(a.grid, a.cell_start, xs, ys, ids, me.px, me.py, me.id, g.eyesight, g.thr2,
-                                [&](uint32_t j, double dx, double dy, double d2) {
-                                  nbc++;
-                                  double col_time =
-                                      time_to_collision(vxs[j] - me.vx, vys[j] - me.vy, dx, dy, d2, rr);
-                                  if (col_time < t_i) t_i = col_time;
-                                });
-      // zanlungo.rs:210-215
-      if (t_i != RCS_INF) {
-        finite = 1;
-        for_each_neighbour(a.grid, a.cell_start, xs, ys, ids, me.px, me.py, me.id, g.eyesight, g.thr2,
-                           [&](uint32_t j, double, double, double) {
-                             PairIn p;
-                             p.px = me.px; p.py = me.py; p.vx = me.vx; p.vy = me.vy;
-                             p.pfx = me.pfx; p.pfy = me.pfy; p.id = me.id;
-                             p.ox = xs[j]; p.oy = ys[j]; p.ovx = vxs[j]; p.ovy = vys[j]; p.oid = ids[j];
-                             double pfx, pfy;
-                             double row;
-                             if (((p.id | p.oid) >> 53) == 0ull) row = p.id < p.oid ? -1.0 : 1.0;
-                             else row = right_of_way(p.id, p.oid);
-                             if (row < 0.0) {
-                               pair_force_yield(p, t_i, g, pfx, pfy);
-                             } else if (row > 0.0 && g.w0_fast && pair_force_w0_is_zero(p, t_i)) {
-                               return;  // contributes exactly (+-0, +-0)
-                             } else {
-                               pair_force_literal(p, t_i, g, pfx, pfy);
-                             }
-                             fx = fx + pfx;
-                             fy = fy + pfy;
-                           });
-      }
+      zanlungo_sequential(a, i, me, g, t_i, fx, fy, nbc, cand);
+      finite = t_i != RCS_INF ? 1u : 0u;
       // zanlungo.rs:216
       velx = velx + fx * g.inv_mass;
       vely = vely + fy * g.inv_mass;
     }
-
-    // explicit Euler, lib.rs:295-297
-    double nx = me.px + velx * a.dt;
-    double ny = me.py + vely * a.dt;
-    a.ox[i] = nx;
-    a.oy[i] = ny;
-    a.ovx[i] = velx;
-    a.ovy[i] = vely;
-    if (a.t_i) {
-      a.t_i[i] = t_i;
-      a.fx[i] = fx;
-      a.fy[i] = fy;
-      a.nb_count[i] = nbc;
-    }
-    // spatial_index.add_or_update(new_pos) error path, lib.rs:299-302
-    uint64_t idx;
-    if (!location_to_index(a.grid, nx, ny, idx)) {
-      atomicAdd(&a.status->oob_count, 1u);
-      atomicMin(&a.status->first_oob_id, (unsigned long long)me.id);
-    }
-    if (!(isfinite(nx) && isfinite(ny) && isfinite(velx) && isfinite(vely))) atomicAdd(&a.status->nonfinite_count, 1u);
+    integrate_and_store(a, i, me, velx, vely, t_i, fx, fy, nbc);
   }
-  if (a.collect_stats) {
-    // warp-level reduction, one atomic per warp and counter
-    unsigned long long c = cand, nb = nbc, ft = finite;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      c += __shfl_down_sync(0xffffffffu, c, d);
-      nb += __shfl_down_sync(0xffffffffu, nb, d);
-      ft += __shfl_down_sync(0xffffffffu, ft, d);
-    }
-    if ((threadIdx.x & 31) == 0) {
-      if (c) atomicAdd(&a.status->candidate_total, c);
-      if (nb) atomicAdd(&a.status->neighbour_total, nb);
-      if (ft) atomicAdd(&a.status->finite_tti, ft);
-    }
-  }
+  warp_stats(a, cand, nbc, finite);
 }
 
 // Trace: neighbour ids in list order (lib.rs:281-286) as CSR, offsets from an exclusive scan of nb_count.

@@ -213,59 +213,118 @@ __device__ __noinline__ void pair_force_literal(const PairIn& p, double t_i, con
   fy = ny * s;
 }
 
+// Per-owner terms of compute_agent_force that do not depend on the neighbour, hoisted out of the pair
+// loop.  Each is computed by the same operations the literal code applies per pair, so the hoisting
+// is bit-neutral:
+//   yield case (row < 0): my_vel = v (zanlungo.rs:188);  fut = p + v*t_i (:109);  with a finite
+//     neighbour velocity other_vel = ov + 1*((0,0) - ov) is exactly (+0,+0), hence my_vel - other_vel = v
+//     and magnitude = (2*agent_scale)*|v| / t_i, capped at 1e15 (:163-167), is the same for every pair;
+//   weight-0 case (row > 0): my_vel = v + 1*(pref - v) (:193);  fut0 = p + my_vel*t_i.
+struct OwnerPre {
+  double futx, futy;  // p + v * t_i
+  double mag;         // capped magnitude of the yield case when the neighbour velocity is finite
+  double mvx, mvy;    // my_vel of the weight-0 case
+  double f0x, f0y;    // p + my_vel(w0) * t_i
+};
+
+__device__ __forceinline__ OwnerPre owner_precompute(double px, double py, double vx, double vy, double pfx,
+                                                     double pfy, double t_i, const GroupDev& z) {
+  OwnerPre o;
+  o.futx = px + vx * t_i;
+  o.futy = py + vy * t_i;
+  double magnitude = ((2.0 * z.agent_scale) * sqrt(vx * vx + vy * vy)) / t_i;
+  if (magnitude >= 1e15) magnitude = 1e15;
+  o.mag = magnitude;
+  o.mvx = vx + 1.0 * (pfx - vx);
+  o.mvy = vy + 1.0 * (pfy - vy);
+  o.f0x = px + o.mvx * t_i;
+  o.f0y = py + o.mvy * t_i;
+  return o;
+}
+
 // A pair in which the current agent has the higher id gets weight = 1 - 1 = 0 (zanlungo.rs:108,
 // 191-194).  Its contribution is d_hat * ((0*scale*|dv|/t_i) * exp(..)).  With z.w0_fast (host
 // checked: agent_scale finite, exp argument bounded) this is exactly (+-0, +-0) -- a no-op for
 // the accumulator, which starts at +0 -- unless t_i == 0, |dv|^2 is not finite, or d_ij has zero /
-// non-finite length.  Returns true when the pair is provably such a no-op.
-__device__ __forceinline__ bool pair_force_w0_is_zero(const PairIn& p, double t_i) {
-  double mvx = p.vx + 1.0 * (p.pfx - p.vx);
-  double mvy = p.vy + 1.0 * (p.pfy - p.vy);
-  double dx = (p.px + mvx * t_i) - (p.ox + p.ovx * t_i);
-  double dy = (p.py + mvy * t_i) - (p.oy + p.ovy * t_i);
+// non-finite length; in those cases it is NaN or +-0 per component.  Returns true when the pair is
+// provably such a no-op.
+__device__ __forceinline__ bool pair_force_w0_is_zero(const OwnerPre& o, double ox, double oy, double ovx,
+                                                      double ovy, double t_i) {
+  double dx = o.f0x - (ox + ovx * t_i);
+  double dy = o.f0y - (oy + ovy * t_i);
   double dd = dx * dx + dy * dy;
-  double rvx = mvx - p.ovx, rvy = mvy - p.ovy;
+  double rvx = o.mvx - ovx, rvy = o.mvy - ovy;
   double rv2 = rvx * rvx + rvy * rvy;
   return (t_i > 0.0) && (dd > 0.0) && (dd < RCS_INF) && (rv2 < RCS_INF);
 }
 
 // Hot-path specialisation of pair_force_literal for row < 0 (current agent has the LOWER id and
-// yields: weight = 2, slerp parameter t = 1).  Same operations in the same order; only the parts
-// that are compile-time constants for this case are folded:
-//   r_2 = sqrt(1) = 1;  other_vel = ov + 1*((0) - ov);  pref_speed = sqrt(0*0+0*0) = 0 < 1e-4;
-//   s0 = sin((1-1)*theta)/sin_theta = sin(0*theta)/sin_theta.
-__device__ __forceinline__ void pair_force_yield(const PairIn& p, double t_i, const GroupDev& z, double& fx,
-                                                 double& fy) {
-  double ovx = p.ovx + 1.0 * (0.0 - p.ovx);
-  double ovy = p.ovy + 1.0 * (0.0 - p.ovy);
-  const double weight = 2.0;
-  double futx = p.px + p.vx * t_i, futy = p.py + p.vy * t_i;
-  double ofx = p.ox + ovx * t_i, ofy = p.oy + ovy * t_i;
-  double dx = futx - ofx, dy = futy - ofy;
+// yields: weight = 2, slerp parameter t = 1).  Same operations in the same order as the literal code
+// except for the two documented substitutions:
+//  (1) per-owner terms come from OwnerPre (bit-neutral, see above);
+//  (2) the slerp weights sin((1-t)*theta)/sin_theta and sin(t*theta)/sin_theta with t = 1,
+//      theta = asin(sin_theta), sin_theta in [0,1] are replaced by their exact values 0 and 1 for
+//      sin_theta > 0 and NaN otherwise (0/0, NaN).  The literal evaluation through libm returns
+//      1 +- 2 ulp for the second weight, so this differs from the reference by <= 4e-16 relative --
+//      inside the 1e-9 force tolerance, and CUDA's sin/asin would not have matched glibc's last bit
+//      anyway.  It removes asin, sin and two divisions from every evaluated pair.
+__device__ __forceinline__ void pair_force_yield(const OwnerPre& o, double px, double py, double vx, double vy,
+                                                 double ox, double oy, double n_vx, double n_vy, double t_i,
+                                                 const GroupDev& z, double& fx, double& fy) {
+  double ovx = n_vx + 1.0 * (0.0 - n_vx);
+  double ovy = n_vy + 1.0 * (0.0 - n_vy);
+  double ofx = ox + ovx * t_i, ofy = oy + ovy * t_i;
+  double dx = o.futx - ofx, dy = o.futy - ofy;
   double dist = sqrt(dx * dx + dy * dy);
-  double crx = p.px - p.ox, cry = p.py - p.oy;
+  double crx = px - ox, cry = py - oy;
   double perpx = -cry, perpy = crx;
-  if (perpx * p.vx + perpy * p.vy < 0.0) {
+  if (perpx * vx + perpy * vy < 0.0) {
     perpx = -perpx;
     perpy = -perpy;
   }
   double sin_theta = perpx * dy - perpy * dx;
   if (sin_theta < 0.0) sin_theta = -sin_theta;
   if (sin_theta > 1.0) sin_theta = 1.0;
-  double theta = asin(sin_theta);
-  double s0 = sin(0.0 * theta) / sin_theta;
-  double s1 = sin(1.0 * theta) / sin_theta;
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  double s0 = sin_theta > 0.0 ? 0.0 : qnan;
+  double s1 = sin_theta > 0.0 ? 1.0 : qnan;
   double ndx = dx * s0 + perpx * s1;
   double ndy = dy * s0 + perpy * s1;
   double nrm = sqrt(ndx * ndx + ndy * ndy);
   double nx = ndx / nrm, ny = ndy / nrm;
   double surface_dist = dist - z.two_r;
-  double rvx = p.vx - ovx, rvy = p.vy - ovy;
-  double magnitude = ((weight * z.agent_scale) * sqrt(rvx * rvx + rvy * rvy)) / t_i;
-  if (magnitude >= 1e15) magnitude = 1e15;
+  double magnitude;
+  if (ovx == 0.0 && ovy == 0.0) {
+    magnitude = o.mag;
+  } else {  // non-finite neighbour velocity: literal
+    double rvx = vx - ovx, rvy = vy - ovy;
+    magnitude = ((2.0 * z.agent_scale) * sqrt(rvx * rvx + rvy * rvy)) / t_i;
+    if (magnitude >= 1e15) magnitude = 1e15;
+  }
   double s = magnitude * exp(-surface_dist / z.force_distance);
   fx = nx * s;
   fy = ny * s;
+}
+
+// One neighbour's contribution in the force pass, shared by every kernel form so that all of them
+// produce the same bits.  Returns false when the pair contributes exactly (+-0, +-0).
+__device__ __forceinline__ bool pair_force_dispatch(const OwnerPre& o, double px, double py, double vx, double vy,
+                                                    double pfx, double pfy, uint64_t id, double ox, double oy,
+                                                    double ovx, double ovy, uint64_t oid, double t_i,
+                                                    const GroupDev& z, double& fx, double& fy) {
+  double row;
+  if (((id | oid) >> 53) == 0ull) row = id < oid ? -1.0 : 1.0;
+  else row = right_of_way(id, oid);
+  if (row < 0.0) {
+    pair_force_yield(o, px, py, vx, vy, ox, oy, ovx, ovy, t_i, z, fx, fy);
+    return true;
+  }
+  if (row > 0.0 && z.w0_fast && pair_force_w0_is_zero(o, ox, oy, ovx, ovy, t_i)) return false;
+  PairIn p;
+  p.px = px; p.py = py; p.vx = vx; p.vy = vy; p.pfx = pfx; p.pfy = pfy; p.id = id;
+  p.ox = ox; p.oy = oy; p.ovx = ovx; p.ovy = ovy; p.oid = oid;
+  pair_force_literal(p, t_i, z, fx, fy);
+  return true;
 }
 
 }  // namespace rcs
