@@ -222,18 +222,31 @@ int rcs_fp64_peak(int32_t device, double* out_tflops, double* out_dadd_tops);
 
 /* ---- multi-GPU spatial strips ------------------------------------------
  * One process per GPU.  Strips are whole cell columns in x (the cell index is x-major,
- * location_hash_2d.rs:59).  rcs_nccl_unique_id is called on rank 0 and the 128 bytes are
- * distributed by the host program (e.g. torch.distributed); rcs_dist_init then builds the NCCL
- * communicator inside the library.  Agents are handed to the rank that owns their column with
- * rcs_add_agents as usual (each rank adds only its own; ids are supplied by rcs_dist_add_agents). */
+ * location_hash_2d.rs:59), so a strip is a contiguous range of cell indices.  Every step a rank sends
+ * the agents of its boundary columns to its two neighbours (NCCL point-to-point over NVLink) and
+ * advances the ghosts of the first column beyond its boundary redundantly, which makes migration
+ * implicit (see rcs_host_dist.inl).  Results are bit-identical for every number of ranks.
+ *
+ * rcs_nccl_unique_id is called on rank 0 and the 128 bytes are distributed by the host program (e.g.
+ * torch.distributed); rcs_dist_init then builds the NCCL communicator inside the library.  It must be
+ * called before agents are added; each rank then adds the agents whose column it owns
+ * (rcs_dist_strip) with rcs_dist_add_agents.  halo_capacity = agents per halo buffer (0: capacity/8).
+ * A failing step (out of bounds, halo overflow, an agent that jumps over the ring) stops the rank and,
+ * through a flag in the halo header, its neighbours within the next steps; the job is then over. */
 int rcs_nccl_unique_id(uint8_t out_id[128]);
-int rcs_dist_init(rcs_sim* sim, int32_t rank, int32_t world, const uint8_t nccl_id[128]);
+int rcs_dist_init(rcs_sim* sim, int32_t rank, int32_t world, const uint8_t nccl_id[128], uint64_t halo_capacity);
 /* Column range [c0, c1) owned by `rank` of `world` for this handle's grid. */
 int rcs_dist_strip(rcs_sim* sim, int32_t rank, int32_t world, uint64_t* c0, uint64_t* c1);
 /* add_agents with caller-supplied global ids (the global sequential allocation of lib.rs:128-129
- * is done by the host program across ranks). */
+ * is done by the host program across ranks) and initial velocities (vxy may be NULL). */
 int rcs_dist_add_agents(rcs_sim* sim, uint64_t n, const uint64_t* ids, const double* xy, const double* vxy,
                         uint32_t hl, uint32_t lp, double eyesight);
+/* Single-process transport: sims[r] is rank r of `world` handles that live in this process (on one
+ * or several devices); halos move with peer copies ordered by events.  The group is stepped as a
+ * whole; rcs_sync / rcs_read_agents / rcs_step_stats work per handle.  Used to test strips on one
+ * GPU with the very kernels the NCCL transport runs. */
+int rcs_dist_init_local(rcs_sim** sims, int32_t world, uint64_t halo_capacity);
+int rcs_dist_step_local(rcs_sim** sims, int32_t world, uint64_t secs, uint32_t nanos, uint32_t flags);
 
 #ifdef __cplusplus
 }

@@ -128,7 +128,9 @@ SIGNATURES = {
     "rcs_launch_count": (C.c_int, [C.c_void_p, c_u64p]),
     "rcs_fp64_peak": (C.c_int, [C.c_int32, c_f64p, c_f64p]),
     "rcs_nccl_unique_id": (C.c_int, [c_u8p]),
-    "rcs_dist_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_u8p]),
+    "rcs_dist_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_u8p, C.c_uint64]),
+    "rcs_dist_init_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_uint64]),
+    "rcs_dist_step_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_uint64, C.c_uint32, C.c_uint32]),
     "rcs_dist_strip": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_u64p, c_u64p]),
     "rcs_dist_add_agents": (
         C.c_int,

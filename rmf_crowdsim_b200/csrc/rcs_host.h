@@ -1,0 +1,187 @@
+// rcs_host.h -- the simulation handle and small host helpers shared by the .inl parts of rcs.cu.
+//
+// One translation unit (rcs.cu) includes the kernels and every host part, so that each __global__
+// function is defined exactly once and the whole library is compiled with --fmad=false.
+#pragma once
+
+#include "../../include/rcs.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "rcs_kernels.cuh"
+#include "rcs_step_warp.cuh"
+
+namespace rcs_host {
+
+using namespace rcs;
+
+struct LPDesc {
+  uint32_t kind;
+  double agent_scale, obstacle_scale, reaction_time, force_distance, agent_mass, agent_radius;
+};
+struct HLDesc {
+  uint32_t kind;
+  double vx, vy;
+  uint32_t route;  // HL_ROUTE: index into the route table
+};
+struct GroupKey {
+  uint32_t hl, lp;
+  double eyesight;
+  int32_t source_sink;
+};
+
+// What rcs_sync needs to undo a failed asynchronous step: the pre-step snapshot of every step on the
+// sorted path is the `srt` buffer set of the moment the step was enqueued.
+struct PendingStep {
+  AgentArrays cur, srt;
+  bool snapshot_in_srt;  // false on the streaming path (snapshot = cur)
+  uint32_t n;
+};
+
+struct HaloMem {
+  void* base = nullptr;  // one allocation: [header 64 B][x][y][vx][vy][id][meta][pvx][pvy], each `cap` entries
+  uint64_t bytes = 0;
+  HaloBuf buf{};
+};
+
+// NCCL entry points, resolved with dlopen at rcs_dist_init (the library itself does not link NCCL, so it
+// loads on boxes without it and single-GPU use never touches it).
+struct Id128 {
+  char internal[128];
+};
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Id128 /* ncclUniqueId, by value */, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+
+}  // namespace rcs_host
+
+struct rcs_sim {
+  rcs_sim_desc desc{};
+  rcs::GridDev grid{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  uint64_t cap = 0;
+  uint32_t n = 0;     // live agents owned by this handle, exact as of the last sync
+  uint32_t n_ub = 0;  // upper bound used to size launches while steps with churn are in flight
+  rcs::AgentArrays cur{}, srt{};
+  uint32_t *cellid = nullptr, *perm = nullptr, *cell_count = nullptr, *cell_start = nullptr, *cursor = nullptr;
+  uint32_t *tile_sums = nullptr, *scan_total = nullptr, *big_list = nullptr, *slow_list = nullptr;
+  uint32_t* srt_cell = nullptr;  // strips: insert cell of every sorted agent
+  uint64_t tile_sums_cap = 0;
+  uint32_t* cnt = nullptr;       // device counters CNT_*
+  uint32_t* h_cnt = nullptr;     // pinned copy
+  bool cnt_dirty = true;         // host changed n: cnt[CNT_CUR] must be rewritten before the next step
+  rcs::GroupDev* d_groups = nullptr;
+  uint32_t d_groups_cap = 0;
+  std::vector<rcs::GroupDev> groups;
+  std::vector<rcs_host::GroupKey> group_keys;
+  bool groups_dirty = false;
+  std::vector<rcs_host::LPDesc> lps;
+  std::vector<rcs_host::HLDesc> hls;
+  bool any_zanlungo = false;
+  bool have_host_hl = false;
+  rcs::DevStatus* d_status = nullptr;
+  rcs::DevStatus* h_status = nullptr;  // pinned
+  uint64_t last_alloc_agent_id = 0;
+  unsigned long long* d_next_id = nullptr;  // device copy of last_alloc_agent_id (source sinks allocate ids)
+  uint64_t max_id_plus1 = 0;
+  bool index_valid = false;  // srt + cell_start describe the current positions
+  // id-addressed access
+  uint32_t *slot_of_id = nullptr, *id_rank = nullptr, *order_by_id = nullptr, *presence = nullptr;
+  uint64_t slot_table_cap = 0;
+  bool slot_valid = false;
+  // trace
+  bool trace = false;
+  double *tr_ti = nullptr, *tr_fx = nullptr, *tr_fy = nullptr;
+  uint32_t *tr_nbc = nullptr, *tr_nbo = nullptr, *tr_own = nullptr;
+  uint64_t *tr_nbids = nullptr, *tr_id = nullptr;
+  uint64_t tr_nbids_cap = 0, tr_nb_total = 0;
+  uint32_t tr_n = 0;
+  bool tr_valid = false;
+  // source sinks
+  std::vector<rcs::SourceSinkDev> sources;  // index = source sink id (removed ones stay with alive = 0)
+  std::vector<double> ss_wp;                // shared waypoint table, interleaved
+  rcs::SourceSinkDev* d_sources = nullptr;
+  double* d_ss_wp = nullptr;
+  uint32_t* d_blocked = nullptr;
+  uint32_t *d_sg_start = nullptr, *d_sg_items = nullptr;
+  rcs::SourceGridDev sgrid{};
+  bool sources_dirty = false;
+  uint32_t n_sources_alive = 0;
+  bool ever_had_sources = false;
+  // events (EventListener::agent_spawned / agent_destroyed)
+  unsigned long long *ev_spawn_id = nullptr, *ev_destroyed = nullptr;
+  double* ev_spawn_xy = nullptr;
+  uint32_t ev_cap = 0;
+  // strips
+  rcs::StripDev strip{};
+  int rank = 0, world = 1;
+  uint32_t halo_width = 0;  // columns sent to each neighbour = ring h + stencil reach q
+  rcs_host::HaloMem send_l, send_r, recv_l, recv_r;
+  void* nccl_comm = nullptr;
+  std::vector<rcs_sim*> local_group;  // single-process transport: the handles of all ranks, by rank
+  cudaEvent_t ev_packed = nullptr, ev_copied = nullptr;
+  // staging
+  void* stage = nullptr;
+  uint64_t stage_bytes = 0;
+  void* flush_buf = nullptr;
+  uint64_t flush_bytes = 0;
+  unsigned int* d_bad = nullptr;
+  unsigned long long* d_bad2 = nullptr;  // 8-byte device scratch
+  std::vector<rcs_host::PendingStep> pending;
+  uint64_t steps_enqueued = 0;
+  unsigned long long* d_steps_done = nullptr;
+  uint64_t steps_done_at_sync = 0;
+  std::string err;
+  uint64_t launches = 0;
+  rcs_stats stats{};
+  cudaEvent_t events[RCS_NUM_EVENTS]{};
+  uint32_t opt_step_kernel = 0;
+  // dominant-kernel timing
+  bool ktiming = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kevents;  // pending pairs
+  std::vector<cudaEvent_t> kevent_pool;
+  double ktime_ms = 0.0;
+  uint64_t ktime_n = 0;
+};
+
+namespace rcs_host {
+
+extern thread_local std::string g_create_error;
+
+#define CU_TRY(sim, call)                                                                         \
+  do {                                                                                            \
+    cudaError_t e__ = (call);                                                                     \
+    if (e__ != cudaSuccess) {                                                                     \
+      (sim)->err = std::string("CUDA error: ") + cudaGetErrorString(e__) + " at " #call;          \
+      return RCS_ERR_CUDA;                                                                        \
+    }                                                                                             \
+  } while (0)
+
+inline uint32_t blocks_for(uint64_t n, uint32_t threads) {
+  return (uint32_t)std::max<uint64_t>((n + threads - 1) / threads, 1);
+}
+
+template <class T>
+inline cudaError_t dalloc(T** p, uint64_t count) {
+  return cudaMalloc(reinterpret_cast<void**>(p), std::max<uint64_t>(count, 1) * sizeof(T));
+}
+
+inline bool churn(const rcs_sim* s) { return s->ever_had_sources || s->strip.enabled; }
+
+}  // namespace rcs_host

@@ -1,0 +1,479 @@
+// rcs_host_api.inl -- handle life cycle, planner descriptors, agents and the pub `agents` view.
+// Part of rcs.cu (single translation unit).
+
+using namespace rcs_host;
+
+static void dist_teardown(rcs_sim* s);
+
+extern "C" {
+
+uint32_t rcs_abi_version(void) { return RCS_ABI_VERSION; }
+
+const char* rcs_last_error(const rcs_sim* sim) { return sim ? sim->err.c_str() : g_create_error.c_str(); }
+
+int rcs_sim_create(const rcs_sim_desc* desc, rcs_sim** out) {
+  if (!desc || !out) {
+    g_create_error = "null argument";
+    return RCS_ERR_ARG;
+  }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                     " (this library has no CPU fallback)";
+    return RCS_ERR_NO_DEVICE;
+  }
+  if (desc->device < 0 || desc->device >= ndev) {
+    g_create_error = "device ordinal out of range";
+    return RCS_ERR_ARG;
+  }
+  rcs_sim* s = new rcs_sim();
+  s->desc = *desc;
+  s->device = desc->device;
+  s->cap = std::max<uint64_t>(desc->capacity, 1);
+  // LocationHash2D::new, location_hash_2d.rs:33-51
+  GridDev& g = s->grid;
+  g.offx = desc->offset_x;
+  g.offy = desc->offset_y;
+  g.res = desc->cell_size;
+  g.nx = host_f64_as_usize(desc->width / desc->cell_size);
+  uint64_t ny = host_f64_as_usize(desc->height / desc->cell_size);
+  if (g.nx != 0 && ny > (0xfffffff0ull / g.nx)) {
+    g_create_error = "grid has more than 2^32 cells";
+    delete s;
+    return RCS_ERR_ARG;
+  }
+  g.len = g.nx * ny;
+  g.x_max = (g.len == 0 || g.nx == 0) ? -1 : (int64_t)((g.len - 1) / g.nx);
+  if (s->cap >= 0xfffffff0ull) {
+    g_create_error = "capacity must be < 2^32";
+    delete s;
+    return RCS_ERR_ARG;
+  }
+  auto fail = [&](int rc) {
+    g_create_error = s->err;
+    rcs_sim_destroy(s);
+    return rc;
+  };
+#define CR_TRY(call)                                                           \
+  do {                                                                         \
+    cudaError_t e__ = (call);                                                  \
+    if (e__ != cudaSuccess) {                                                  \
+      s->err = std::string("CUDA error: ") + cudaGetErrorString(e__) + " at " #call; \
+      return fail(RCS_ERR_CUDA);                                               \
+    }                                                                          \
+  } while (0)
+  CR_TRY(cudaSetDevice(s->device));
+  CR_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  if (alloc_agent_arrays(s, s->cur, s->cap) || alloc_agent_arrays(s, s->srt, s->cap)) return fail(RCS_ERR_CUDA);
+  CR_TRY(dalloc(&s->cellid, s->cap + 16));
+  CR_TRY(dalloc(&s->perm, s->cap + 16));
+  CR_TRY(dalloc(&s->order_by_id, s->cap + 16));
+  CR_TRY(dalloc(&s->cell_count, g.len + 16));
+  CR_TRY(dalloc(&s->cell_start, g.len + 16));
+  CR_TRY(dalloc(&s->cursor, g.len + 16));
+  CR_TRY(dalloc(&s->scan_total, 4));
+  CR_TRY(dalloc(&s->big_list, 4096));
+  CR_TRY(dalloc(&s->slow_list, s->cap + 16));
+  CR_TRY(dalloc(&s->cnt, CNT_N));
+  CR_TRY(dalloc(&s->d_next_id, 1));
+  CR_TRY(cudaMemset(s->cnt, 0, CNT_N * sizeof(uint32_t)));
+  CR_TRY(cudaMemset(s->d_next_id, 0, sizeof(unsigned long long)));
+  CR_TRY(cudaMallocHost(reinterpret_cast<void**>(&s->h_cnt), CNT_N * sizeof(uint32_t)));
+  std::memset(s->h_cnt, 0, CNT_N * sizeof(uint32_t));
+  CR_TRY(dalloc(&s->d_status, 1));
+  CR_TRY(dalloc(&s->d_steps_done, 1));
+  CR_TRY(dalloc(&s->d_bad, 1));
+  CR_TRY(dalloc(&s->d_bad2, 1));
+  CR_TRY(cudaMemset(s->d_status, 0, sizeof(DevStatus)));
+  CR_TRY(cudaMemset(s->d_steps_done, 0, sizeof(unsigned long long)));
+  CR_TRY(cudaMemset(s->scan_total, 0xff, 4 * sizeof(uint32_t)));
+  CR_TRY(cudaMemset(s->cell_start, 0, (g.len + 16) * sizeof(uint32_t)));
+  CR_TRY(cudaMallocHost(reinterpret_cast<void**>(&s->h_status), sizeof(DevStatus)));
+  for (uint32_t k = 0; k < RCS_NUM_EVENTS; ++k) CR_TRY(cudaEventCreate(&s->events[k]));
+#undef CR_TRY
+  s->stats.first_oob_id = ~0ull;
+  *out = s;
+  return RCS_OK;
+}
+
+void rcs_sim_destroy(rcs_sim* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  free_agent_arrays(s->cur);
+  free_agent_arrays(s->srt);
+  cudaFree(s->cellid); cudaFree(s->perm); cudaFree(s->order_by_id); cudaFree(s->cell_count);
+  cudaFree(s->cell_start); cudaFree(s->cursor); cudaFree(s->tile_sums); cudaFree(s->scan_total);
+  cudaFree(s->big_list); cudaFree(s->d_groups); cudaFree(s->d_status); cudaFree(s->d_steps_done);
+  cudaFree(s->d_bad); cudaFree(s->d_bad2); cudaFree(s->slot_of_id); cudaFree(s->id_rank); cudaFree(s->presence);
+  cudaFree(s->tr_ti); cudaFree(s->tr_fx); cudaFree(s->tr_fy); cudaFree(s->tr_nbc); cudaFree(s->tr_nbo);
+  cudaFree(s->tr_nbids); cudaFree(s->tr_id); cudaFree(s->tr_own); cudaFree(s->stage); cudaFree(s->flush_buf);
+  cudaFree(s->slow_list); cudaFree(s->cnt); cudaFree(s->d_next_id); cudaFree(s->srt_cell);
+  cudaFree(s->d_sources); cudaFree(s->d_ss_wp); cudaFree(s->d_blocked); cudaFree(s->d_sg_start);
+  cudaFree(s->d_sg_items); cudaFree(s->ev_spawn_id); cudaFree(s->ev_destroyed); cudaFree(s->ev_spawn_xy);
+  dist_teardown(s);
+  if (s->h_status) cudaFreeHost(s->h_status);
+  if (s->h_cnt) cudaFreeHost(s->h_cnt);
+  for (uint32_t k = 0; k < RCS_NUM_EVENTS; ++k)
+    if (s->events[k]) cudaEventDestroy(s->events[k]);
+  for (auto& pr : s->kevents) {
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  for (auto e : s->kevent_pool) cudaEventDestroy(e);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+int rcs_lp_none(rcs_sim* s, uint32_t* out_lp) {
+  if (!s || !out_lp) return RCS_ERR_ARG;
+  s->lps.push_back(LPDesc{LP_NONE, 0, 0, 0, 0, 0, 0});
+  *out_lp = (uint32_t)s->lps.size() - 1;
+  return RCS_OK;
+}
+
+int rcs_lp_zanlungo(rcs_sim* s, double agent_scale, double obstacle_scale, double reaction_time, double force_distance,
+                    double agent_mass, double agent_radius, uint32_t* out_lp) {
+  if (!s || !out_lp) return RCS_ERR_ARG;
+  s->lps.push_back(LPDesc{LP_ZANLUNGO, agent_scale, obstacle_scale, reaction_time, force_distance, agent_mass,
+                          agent_radius});
+  *out_lp = (uint32_t)s->lps.size() - 1;
+  return RCS_OK;
+}
+
+static int push_hl(rcs_sim* s, uint32_t kind, double vx, double vy, uint32_t* out_hl) {
+  if (!s || !out_hl) return RCS_ERR_ARG;
+  s->hls.push_back(HLDesc{kind, vx, vy, 0u});
+  *out_hl = (uint32_t)s->hls.size() - 1;
+  return RCS_OK;
+}
+int rcs_hl_constant(rcs_sim* s, double vx, double vy, uint32_t* out_hl) { return push_hl(s, HL_CONSTANT, vx, vy, out_hl); }
+int rcs_hl_parity(rcs_sim* s, double vx, double vy, uint32_t* out_hl) { return push_hl(s, HL_PARITY, vx, vy, out_hl); }
+int rcs_hl_none(rcs_sim* s, uint32_t* out_hl) { return push_hl(s, HL_NONE, 0, 0, out_hl); }
+int rcs_hl_host(rcs_sim* s, uint32_t* out_hl) {
+  if (!s || !out_hl) return RCS_ERR_ARG;
+  CU_TRY(s, cudaSetDevice(s->device));
+  int rc = do_sync(s);
+  if (rc) return rc;
+  rc = ensure_pref_arrays(s);
+  if (rc) return rc;
+  s->have_host_hl = true;
+  return push_hl(s, HL_HOST, 0, 0, out_hl);
+}
+
+static int add_agents_impl(rcs_sim* s, uint64_t n, const uint64_t* ids, const double* xy, const double* vxy,
+                           uint32_t hl, uint32_t lp, double eyesight, int32_t source_sink, uint64_t* out_ids) {
+  if (!s || (n && !xy)) return RCS_ERR_ARG;
+  if (hl >= s->hls.size() || lp >= s->lps.size()) {
+    s->err = "unknown planner handle";
+    return RCS_ERR_ARG;
+  }
+  CU_TRY(s, cudaSetDevice(s->device));
+  if ((uint64_t)s->n + n > s->cap) {
+    s->err = "capacity exceeded";
+    return RCS_ERR_CAPACITY;
+  }
+  // location_to_index of every spawn position first (lib.rs:146-149)
+  for (uint64_t k = 0; k < n; ++k) {
+    uint64_t idx;
+    if (!host_location_to_index(s->grid, xy[2 * k], xy[2 * k + 1], idx)) {
+      s->err = "Index out of bounds";
+      return RCS_ERR_OUT_OF_BOUNDS;
+    }
+  }
+  if (s->strip.enabled) {
+    for (uint64_t k = 0; k < n; ++k) {
+      uint64_t cx = host_f64_as_usize((xy[2 * k] - s->grid.offx) / s->grid.res);
+      if (cx < s->strip.c0 || cx >= s->strip.c1) {
+        s->err = "agent position is outside this rank's strip";
+        return RCS_ERR_ARG;
+      }
+    }
+  }
+  if (n == 0) return RCS_OK;
+  int rc = do_sync(s);
+  if (rc) return rc;
+  uint32_t grp = find_or_add_group(s, hl, lp, eyesight, source_sink);
+  std::vector<double> hx(n), hy(n), hvx(n, 0.0), hvy(n, 0.0);
+  std::vector<uint64_t> hid(n);
+  std::vector<uint32_t> hgrp(n, grp), hwp(n, 0u);
+  for (uint64_t k = 0; k < n; ++k) {
+    hx[k] = xy[2 * k];
+    hy[k] = xy[2 * k + 1];
+    if (vxy) {
+      hvx[k] = vxy[2 * k];
+      hvy[k] = vxy[2 * k + 1];
+    }
+    if (ids) {
+      hid[k] = ids[k];
+      s->max_id_plus1 = std::max(s->max_id_plus1, ids[k] + 1);
+    } else {
+      hid[k] = s->last_alloc_agent_id++;  // lib.rs:128-129
+    }
+    if (out_ids) out_ids[k] = hid[k];
+  }
+  if (!ids) s->max_id_plus1 = std::max(s->max_id_plus1, s->last_alloc_agent_id);
+  const uint32_t o = s->n;
+  CU_TRY(s, cudaMemcpy(s->cur.x + o, hx.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+  CU_TRY(s, cudaMemcpy(s->cur.y + o, hy.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+  CU_TRY(s, cudaMemcpy(s->cur.vx + o, hvx.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+  CU_TRY(s, cudaMemcpy(s->cur.vy + o, hvy.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+  CU_TRY(s, cudaMemcpy(s->cur.id + o, hid.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  CU_TRY(s, cudaMemcpy(s->cur.grp + o, hgrp.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  CU_TRY(s, cudaMemcpy(s->cur.wp + o, hwp.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  if (s->cur.pvx) {
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    fill_f64_kernel<<<blocks_for(n, 256), 256, 0, s->stream>>>(n, s->cur.pvx + o, nan);
+    fill_f64_kernel<<<blocks_for(n, 256), 256, 0, s->stream>>>(n, s->cur.pvy + o, nan);
+    s->launches += 2;
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+  }
+  s->n += (uint32_t)n;
+  s->n_ub = s->n;
+  s->cnt_dirty = true;
+  if (!ids) {
+    unsigned long long next = s->last_alloc_agent_id;
+    CU_TRY(s, cudaMemcpy(s->d_next_id, &next, sizeof(next), cudaMemcpyHostToDevice));
+  }
+  invalidate(s);
+  return RCS_OK;
+}
+
+int rcs_add_agents(rcs_sim* s, uint64_t n, const double* xy, uint32_t hl, uint32_t lp, double eyesight,
+                   uint64_t* out_ids) {
+  return add_agents_impl(s, n, nullptr, xy, nullptr, hl, lp, eyesight, -1, out_ids);
+}
+
+int rcs_dist_add_agents(rcs_sim* s, uint64_t n, const uint64_t* ids, const double* xy, const double* vxy, uint32_t hl,
+                        uint32_t lp, double eyesight) {
+  if (n && !ids) return RCS_ERR_ARG;
+  return add_agents_impl(s, n, ids, xy, vxy, hl, lp, eyesight, -1, nullptr);
+}
+
+int rcs_agent_count(rcs_sim* s, uint64_t* out_n) {
+  if (!s || !out_n) return RCS_ERR_ARG;
+  CU_TRY(s, cudaSetDevice(s->device));
+  int rc = do_sync(s);
+  *out_n = s->n;
+  return rc;
+}
+
+// keep[i] for the removal compaction
+__global__ void mark_remove_kernel(uint32_t m, const uint64_t* __restrict__ ids, const uint32_t* __restrict__ slot_of_id,
+                                   uint64_t table_len, uint32_t* __restrict__ keep, unsigned int* bad) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m) return;
+  uint64_t v = ids[k];
+  uint32_t sl = v < table_len ? slot_of_id[v] : 0xffffffffu;
+  if (sl == 0xffffffffu) {
+    atomicAdd(bad, 1u);
+    return;
+  }
+  keep[sl] = 0u;
+}
+
+__global__ void compact_kernel(uint32_t n, const uint32_t* __restrict__ keep, const uint32_t* __restrict__ pos,
+                               AgentArrays in, AgentArrays out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !keep[i]) return;
+  uint32_t k = pos[i];
+  out.x[k] = in.x[i];
+  out.y[k] = in.y[i];
+  out.vx[k] = in.vx[i];
+  out.vy[k] = in.vy[i];
+  out.id[k] = in.id[i];
+  out.grp[k] = in.grp[i];
+  out.wp[k] = in.wp[i];
+  if (in.pvx) {
+    out.pvx[k] = in.pvx[i];
+    out.pvy[k] = in.pvy[i];
+  }
+}
+
+int rcs_remove_agents(rcs_sim* s, uint64_t m, const uint64_t* ids) {
+  if (!s || (m && !ids)) return RCS_ERR_ARG;
+  if (m == 0) return RCS_OK;
+  CU_TRY(s, cudaSetDevice(s->device));
+  int rc = do_sync(s);
+  if (rc) return rc;
+  rc = build_slot_table(s);
+  if (rc) return rc;
+  rc = ensure_stage(s, m * sizeof(uint64_t));
+  if (rc) return rc;
+  uint64_t* d_ids = static_cast<uint64_t*>(s->stage);
+  CU_TRY(s, cudaMemcpyAsync(d_ids, ids, m * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
+  CU_TRY(s, cudaMemsetAsync(s->d_bad, 0, sizeof(unsigned int), s->stream));
+  uint32_t n = s->n;
+  fill_u32_kernel<<<blocks_for(n, 256), 256, 0, s->stream>>>(n, s->cellid, 1u);
+  mark_remove_kernel<<<blocks_for(m, 256), 256, 0, s->stream>>>((uint32_t)m, d_ids, s->slot_of_id,
+                                                                std::max<uint64_t>(s->max_id_plus1, 1), s->cellid,
+                                                                s->d_bad);
+  s->launches += 2;
+  unsigned int bad = 0;
+  CU_TRY(s, cudaMemcpyAsync(&bad, s->d_bad, sizeof(bad), cudaMemcpyDeviceToHost, s->stream));
+  CU_TRY(s, cudaStreamSynchronize(s->stream));
+  if (bad) {
+    s->err = "unknown agent id";
+    return RCS_ERR_ARG;
+  }
+  rc = exclusive_scan(s, s->cellid, n, s->perm, nullptr);
+  if (rc) return rc;
+  compact_kernel<<<blocks_for(n, 256), 256, 0, s->stream>>>(n, s->cellid, s->perm, s->cur, s->srt);
+  s->launches += 1;
+  uint32_t kept = 0;
+  CU_TRY(s, cudaMemcpyAsync(&kept, s->perm + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  CU_TRY(s, cudaStreamSynchronize(s->stream));
+  std::swap(s->cur, s->srt);
+  s->n = kept;
+  s->n_ub = kept;
+  s->cnt_dirty = true;
+  invalidate(s);
+  return RCS_OK;
+}
+
+int rcs_set_state(rcs_sim* s, uint64_t m, const uint64_t* ids, const double* x, const double* y, const double* vx,
+                  const double* vy) {
+  if (!s) return RCS_ERR_ARG;
+  if (m == 0) return RCS_OK;
+  CU_TRY(s, cudaSetDevice(s->device));
+  int rc = do_sync(s);
+  if (rc) return rc;
+  if (!ids && m != s->n) {
+    s->err = "ids == NULL requires n == agent count";
+    return RCS_ERR_ARG;
+  }
+  // the reference's index rejects out-of-grid positions (add_or_update, location_hash_2d.rs:126-130)
+  if (x && y) {
+    for (uint64_t k = 0; k < m; ++k) {
+      uint64_t idx;
+      if (!host_location_to_index(s->grid, x[k], y[k], idx)) {
+        s->err = "Index out of bounds";
+        return RCS_ERR_OUT_OF_BOUNDS;
+      }
+    }
+  }
+  rc = build_slot_table(s);
+  if (rc) return rc;
+  rc = ensure_stage(s, m * (sizeof(uint64_t) + sizeof(double)));
+  if (rc) return rc;
+  uint64_t* d_ids = nullptr;
+  double* d_val = reinterpret_cast<double*>(static_cast<char*>(s->stage));
+  if (ids) {
+    d_ids = reinterpret_cast<uint64_t*>(static_cast<char*>(s->stage) + m * sizeof(double));
+    CU_TRY(s, cudaMemcpyAsync(d_ids, ids, m * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
+  }
+  CU_TRY(s, cudaMemsetAsync(s->d_bad, 0, sizeof(unsigned int), s->stream));
+  const double* srcs[4] = {x, y, vx, vy};
+  double* dsts[4] = {s->cur.x, s->cur.y, s->cur.vx, s->cur.vy};
+  for (int a = 0; a < 4; ++a) {
+    if (!srcs[a]) continue;
+    CU_TRY(s, cudaMemcpyAsync(d_val, srcs[a], m * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    scatter_by_id_kernel<double><<<blocks_for(m, 256), 256, 0, s->stream>>>(
+        (uint32_t)m, s->order_by_id, d_ids, s->slot_of_id, std::max<uint64_t>(s->max_id_plus1, 1), d_val, 1, dsts[a],
+        s->d_bad);
+    s->launches += 1;
+  }
+  unsigned int bad = 0;
+  CU_TRY(s, cudaMemcpyAsync(&bad, s->d_bad, sizeof(bad), cudaMemcpyDeviceToHost, s->stream));
+  CU_TRY(s, cudaStreamSynchronize(s->stream));
+  s->index_valid = false;
+  s->tr_valid = false;
+  if (bad) {
+    s->err = "unknown agent id";
+    return RCS_ERR_ARG;
+  }
+  return RCS_OK;
+}
+
+int rcs_set_preferred_velocity(rcs_sim* s, uint64_t m, const uint64_t* ids, const double* vxy) {
+  if (!s || (m && !vxy)) return RCS_ERR_ARG;
+  if (m == 0) return RCS_OK;
+  CU_TRY(s, cudaSetDevice(s->device));
+  if (!s->cur.pvx) {
+    s->err = "no rcs_hl_host planner exists on this handle";
+    return RCS_ERR_ARG;
+  }
+  if (!ids && m != s->n) {
+    s->err = "ids == NULL requires n == agent count";
+    return RCS_ERR_ARG;
+  }
+  int rc = build_slot_table(s);
+  if (rc) return rc;
+  rc = ensure_stage(s, m * (sizeof(uint64_t) + 2 * sizeof(double)));
+  if (rc) return rc;
+  double* d_val = reinterpret_cast<double*>(static_cast<char*>(s->stage));
+  uint64_t* d_ids = nullptr;
+  CU_TRY(s, cudaMemcpyAsync(d_val, vxy, 2 * m * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  if (ids) {
+    d_ids = reinterpret_cast<uint64_t*>(static_cast<char*>(s->stage) + 2 * m * sizeof(double));
+    CU_TRY(s, cudaMemcpyAsync(d_ids, ids, m * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
+  }
+  CU_TRY(s, cudaMemsetAsync(s->d_bad, 0, sizeof(unsigned int), s->stream));
+  const uint64_t L = std::max<uint64_t>(s->max_id_plus1, 1);
+  scatter_by_id_kernel<double><<<blocks_for(m, 256), 256, 0, s->stream>>>((uint32_t)m, s->order_by_id, d_ids,
+                                                                          s->slot_of_id, L, d_val, 2, s->cur.pvx,
+                                                                          s->d_bad);
+  scatter_by_id_kernel<double><<<blocks_for(m, 256), 256, 0, s->stream>>>((uint32_t)m, s->order_by_id, d_ids,
+                                                                          s->slot_of_id, L, d_val + 1, 2, s->cur.pvy,
+                                                                          s->d_bad);
+  s->launches += 2;
+  CU_TRY(s, cudaGetLastError());
+  if (ids) {
+    unsigned int bad = 0;
+    CU_TRY(s, cudaMemcpyAsync(&bad, s->d_bad, sizeof(bad), cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    if (bad) {
+      s->err = "unknown agent id";
+      return RCS_ERR_ARG;
+    }
+  }
+  // the stage buffer is reused by later calls on the same stream: stream order keeps this safe
+  return RCS_OK;
+}
+
+int rcs_read_agents(rcs_sim* s, uint32_t order, uint64_t cap, uint64_t* ids, double* x, double* y, double* vx,
+                    double* vy, uint32_t* next_waypoint, uint64_t* out_n) {
+  if (!s) return RCS_ERR_ARG;
+  CU_TRY(s, cudaSetDevice(s->device));
+  int rc = do_sync(s);
+  if (out_n) *out_n = s->n;
+  if (rc) return rc;
+  uint32_t n = s->n;
+  if (n == 0) return RCS_OK;
+  if (cap < n) {
+    s->err = "output capacity too small";
+    return RCS_ERR_CAPACITY;
+  }
+  const uint32_t* ord = nullptr;
+  if (order == RCS_ORDER_ID) {
+    rc = build_slot_table(s);
+    if (rc) return rc;
+    ord = s->order_by_id;
+  }
+  if (!ord) {
+    // storage order: straight copies
+    if (ids) CU_TRY(s, cudaMemcpyAsync(ids, s->cur.id, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+    if (x) CU_TRY(s, cudaMemcpyAsync(x, s->cur.x, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (y) CU_TRY(s, cudaMemcpyAsync(y, s->cur.y, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (vx) CU_TRY(s, cudaMemcpyAsync(vx, s->cur.vx, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (vy) CU_TRY(s, cudaMemcpyAsync(vy, s->cur.vy, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (next_waypoint)
+      CU_TRY(s, cudaMemcpyAsync(next_waypoint, s->cur.wp, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  } else {
+    rc = ensure_stage(s, (uint64_t)n * 48 + 256);
+    if (rc) return rc;
+    uint64_t off = 0;
+    if (ids) { rc = read_array<uint64_t>(s, s->cur.id, ord, n, ids, off); off += (uint64_t)n * 8; if (rc) return rc; }
+    if (x) { rc = read_array<double>(s, s->cur.x, ord, n, x, off); off += (uint64_t)n * 8; if (rc) return rc; }
+    if (y) { rc = read_array<double>(s, s->cur.y, ord, n, y, off); off += (uint64_t)n * 8; if (rc) return rc; }
+    if (vx) { rc = read_array<double>(s, s->cur.vx, ord, n, vx, off); off += (uint64_t)n * 8; if (rc) return rc; }
+    if (vy) { rc = read_array<double>(s, s->cur.vy, ord, n, vy, off); off += (uint64_t)n * 8; if (rc) return rc; }
+    if (next_waypoint) { rc = read_array<uint32_t>(s, s->cur.wp, ord, n, next_waypoint, off); if (rc) return rc; }
+  }
+  CU_TRY(s, cudaStreamSynchronize(s->stream));
+  return RCS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,418 @@
+// rcs_host_core.inl -- device memory, groups, the index rebuild and rcs_sync of a simulation handle.
+// Part of rcs.cu (single translation unit).
+
+namespace rcs_host {
+
+thread_local std::string g_create_error;
+
+// Rust `f64 as usize` on the host (same rule as rcs_math.cuh)
+static uint64_t host_f64_as_usize(double v) {
+  if (!(v > 0.0)) return 0;
+  if (v >= 18446744073709551616.0) return std::numeric_limits<uint64_t>::max();
+  return (uint64_t)v;
+}
+
+static int64_t host_floor_as_i64(double v) {
+  v = std::floor(v);
+  if (v != v) return 0;
+  if (v >= 9223372036854775808.0) return std::numeric_limits<int64_t>::max();
+  if (v <= -9223372036854775808.0) return std::numeric_limits<int64_t>::min();
+  return (int64_t)v;
+}
+
+static bool host_location_to_index(const GridDev& g, double px, double py, uint64_t& idx) {
+  uint64_t x_idx = host_f64_as_usize((px - g.offx) / g.res);
+  uint64_t y_idx = host_f64_as_usize((py - g.offy) / g.res);
+  idx = x_idx * g.nx + y_idx;
+  return idx < g.len;
+}
+
+// Smallest double T such that sqrt(T) >= R (correctly rounded sqrt is monotone), so that the
+// reference's strict test `norm < radius` (location_hash_2d.rs:251) is exactly `norm_squared < T`.
+static double radius_threshold(double R) {
+  if (R != R) return R;           // NaN: every comparison false, as in the reference
+  if (!(R > 0.0)) return 0.0;     // sqrt(d2) >= 0 is never < R
+  if (std::isinf(R)) return R;    // d2 < inf  <=>  sqrt(d2) < inf
+  double t = R * R;
+  if (std::isinf(t)) {            // R*R overflows: walk down from the largest finite double
+    t = std::numeric_limits<double>::max();
+    if (std::sqrt(t) < R) return std::numeric_limits<double>::infinity();
+  }
+  while (std::sqrt(t) >= R) t = std::nextafter(t, 0.0);
+  while (std::sqrt(t) < R) t = std::nextafter(t, std::numeric_limits<double>::infinity());
+  return t;
+}
+
+static int alloc_agent_arrays(rcs_sim* s, AgentArrays& a, uint64_t cap) {
+  CU_TRY(s, dalloc(&a.x, cap));
+  CU_TRY(s, dalloc(&a.y, cap));
+  CU_TRY(s, dalloc(&a.vx, cap));
+  CU_TRY(s, dalloc(&a.vy, cap));
+  CU_TRY(s, dalloc(&a.id, cap));
+  CU_TRY(s, dalloc(&a.grp, cap));
+  CU_TRY(s, dalloc(&a.wp, cap));
+  a.pvx = a.pvy = nullptr;
+  return RCS_OK;
+}
+
+static void free_agent_arrays(AgentArrays& a) {
+  cudaFree(a.x); cudaFree(a.y); cudaFree(a.vx); cudaFree(a.vy);
+  cudaFree(a.id); cudaFree(a.grp); cudaFree(a.wp); cudaFree(a.pvx); cudaFree(a.pvy);
+  a = AgentArrays{};
+}
+
+static int ensure_stage(rcs_sim* s, uint64_t bytes) {
+  if (bytes <= s->stage_bytes) return RCS_OK;
+  CU_TRY(s, cudaStreamSynchronize(s->stream));
+  if (s->stage) cudaFree(s->stage);
+  s->stage = nullptr;
+  s->stage_bytes = 0;
+  uint64_t want = bytes + bytes / 4 + 4096;
+  CU_TRY(s, cudaMalloc(&s->stage, want));
+  s->stage_bytes = want;
+  return RCS_OK;
+}
+
+// exclusive scan of in[0..len) into out[0..len] (len+1 entries), optional cursor copy
+static int exclusive_scan(rcs_sim* s, const uint32_t* in, uint64_t len, uint32_t* out, uint32_t* cursor) {
+  if (len == 0) {
+    CU_TRY(s, cudaMemsetAsync(out, 0, sizeof(uint32_t), s->stream));
+    return RCS_OK;
+  }
+  uint64_t tiles = (len + SCAN_TILE - 1) / SCAN_TILE;
+  if (tiles > s->tile_sums_cap) {
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    cudaFree(s->tile_sums);
+    s->tile_sums = nullptr;
+    CU_TRY(s, dalloc(&s->tile_sums, tiles + 1024));
+    s->tile_sums_cap = tiles + 1024;
+  }
+  scan_reduce_kernel<<<(uint32_t)tiles, SCAN_THREADS, 0, s->stream>>>(in, len, s->tile_sums);
+  scan_tile_sums_kernel<<<1, SCAN_THREADS, 0, s->stream>>>(s->tile_sums, (uint32_t)tiles, s->scan_total);
+  scan_apply_kernel<<<(uint32_t)tiles, SCAN_THREADS, 0, s->stream>>>(in, len, s->tile_sums, out, cursor);
+  s->launches += 3;
+  CU_TRY(s, cudaGetLastError());
+  return RCS_OK;
+}
+
+static int upload_groups(rcs_sim* s) {
+  if (!s->groups_dirty) return RCS_OK;
+  if (s->groups.size() > s->d_groups_cap) {
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    cudaFree(s->d_groups);
+    s->d_groups = nullptr;
+    uint32_t cap = (uint32_t)s->groups.size() * 2 + 16;
+    CU_TRY(s, dalloc(&s->d_groups, cap));
+    s->d_groups_cap = cap;
+  }
+  // groups is a host vector that may be reallocated later: synchronous copy
+  CU_TRY(s, cudaStreamSynchronize(s->stream));
+  CU_TRY(s, cudaMemcpy(s->d_groups, s->groups.data(), s->groups.size() * sizeof(GroupDev), cudaMemcpyHostToDevice));
+  s->groups_dirty = false;
+  return RCS_OK;
+}
+
+static uint32_t find_or_add_group(rcs_sim* s, uint32_t hl, uint32_t lp, double eyesight, int32_t source_sink) {
+  for (size_t k = 0; k < s->group_keys.size(); ++k) {
+    const GroupKey& g = s->group_keys[k];
+    if (g.hl == hl && g.lp == lp && g.source_sink == source_sink &&
+        std::memcmp(&g.eyesight, &eyesight, sizeof(double)) == 0)
+      return (uint32_t)k;
+  }
+  const LPDesc& L = s->lps[lp];
+  const HLDesc& H = s->hls[hl];
+  GroupDev g{};
+  g.eyesight = eyesight;
+  g.thr2 = radius_threshold(eyesight);
+  g.hl_vx = H.vx;
+  g.hl_vy = H.vy;
+  g.hl_kind = H.kind;
+  g.lp_kind = L.kind;
+  g.source_sink = source_sink;
+  if (L.kind == LP_ZANLUNGO) {
+    g.agent_scale = L.agent_scale;
+    g.force_distance = L.force_distance;
+    g.inv_mass = 1.0 / L.agent_mass;
+    g.rr = L.agent_radius * L.agent_radius;
+    g.two_r = L.agent_radius * 2.0;
+    // weight-0 pairs can be skipped only if 0*agent_scale == 0 and exp(-(dist - 2r)/D) cannot overflow
+    bool ok = std::isfinite(L.agent_scale) && L.force_distance > 0.0 && std::isfinite(g.two_r) &&
+              (g.two_r / L.force_distance) < 700.0;
+    g.w0_fast = ok ? 1u : 0u;
+    s->any_zanlungo = true;
+  }
+  s->groups.push_back(g);
+  s->group_keys.push_back(GroupKey{hl, lp, eyesight, source_sink});
+  s->groups_dirty = true;
+  return (uint32_t)(s->groups.size() - 1);
+}
+
+static int ensure_pref_arrays(rcs_sim* s) {
+  if (s->cur.pvx) return RCS_OK;
+  CU_TRY(s, cudaStreamSynchronize(s->stream));
+  const double nan = std::numeric_limits<double>::quiet_NaN();
+  for (AgentArrays* a : {&s->cur, &s->srt}) {
+    CU_TRY(s, dalloc(&a->pvx, s->cap));
+    CU_TRY(s, dalloc(&a->pvy, s->cap));
+    fill_f64_kernel<<<blocks_for(s->cap, 256), 256, 0, s->stream>>>(s->cap, a->pvx, nan);
+    fill_f64_kernel<<<blocks_for(s->cap, 256), 256, 0, s->stream>>>(s->cap, a->pvy, nan);
+    s->launches += 2;
+  }
+  CU_TRY(s, cudaGetLastError());
+  // pointer roles recorded for pending steps are stale now, but ensure_pref_arrays only runs right after a sync
+  return RCS_OK;
+}
+
+static void invalidate(rcs_sim* s) {
+  s->index_valid = false;
+  s->slot_valid = false;
+  s->tr_valid = false;
+}
+
+// The host changed the agent count (add / remove / rollback): rewrite the device counters.
+static int upload_counts(rcs_sim* s) {
+  if (!s->cnt_dirty) return RCS_OK;
+  set_counts_kernel<<<1, 1, 0, s->stream>>>(s->cnt, s->n);
+  s->launches += 1;
+  CU_TRY(s, cudaGetLastError());
+  s->cnt_dirty = false;
+  return RCS_OK;
+}
+
+// A1/A2 of SURVEY.md section 8a.  Bins the agents [first, cnt[CNT_TOT]) of `cur` into the histogram
+// (which the caller has zeroed, or which already holds the owned agents of a strip).
+static int bin_agents(rcs_sim* s, uint32_t n_ub, const uint32_t* first) {
+  if (!n_ub) return RCS_OK;
+  bin_count_kernel<<<blocks_for(n_ub, 256), 256, 0, s->stream>>>(s->grid, n_ub, first, s->cnt + CNT_TOT, s->cur.x,
+                                                                 s->cur.y, s->cellid, s->cell_count, s->d_status);
+  s->launches += 1;
+  CU_TRY(s, cudaGetLastError());
+  return RCS_OK;
+}
+
+// Histogram -> exclusive scan -> permutation scatter -> ascending-id order inside each cell -> physical
+// reorder of `cur` into `srt`.  cell_start[len] is the number of sorted (in-bounds) agents.
+static int sort_into_srt(rcs_sim* s, uint32_t n_ub) {
+  const uint64_t len = s->grid.len;
+  int rc = exclusive_scan(s, s->cell_count, len, s->cell_start, s->cursor);
+  if (rc) return rc;
+  if (n_ub) {
+    scatter_perm_kernel<<<blocks_for(n_ub, 256), 256, 0, s->stream>>>(n_ub, s->cnt + CNT_TOT, s->cellid, s->cursor,
+                                                                      s->perm, s->d_status);
+    if (len)
+      sort_cells_by_id_kernel<<<blocks_for(len, 128), 128, 0, s->stream>>>(len, s->cell_start, s->cur.id, s->perm,
+                                                                           s->big_list, 4096, s->d_status);
+    sort_big_cells_kernel<<<64, 256, 0, s->stream>>>(s->cell_start, s->cur.id, s->perm, s->slow_list, s->big_list,
+                                                     4096, s->d_status);
+    gather_sorted_kernel<<<blocks_for(n_ub, 256), 256, 0, s->stream>>>(
+        n_ub, s->perm, s->cur, s->srt, s->cellid, s->strip.enabled ? s->srt_cell : nullptr, s->cell_start + len,
+        s->d_status);
+    s->launches += 4;
+  }
+  CU_TRY(s, cudaGetLastError());
+  return RCS_OK;
+}
+
+// (Re)build the canonical (cell, id) sorted copy `srt` of `cur` and cell_start (no step in flight).
+static int build_index(rcs_sim* s) {
+  int rc = upload_counts(s);
+  if (rc) return rc;
+  CU_TRY(s, cudaMemsetAsync(s->cell_count, 0, (s->grid.len + 1) * sizeof(uint32_t), s->stream));
+  rc = bin_agents(s, s->n, nullptr);
+  if (rc) return rc;
+  return sort_into_srt(s, s->n);
+}
+
+static cudaEvent_t kevent_get(rcs_sim* s) {
+  if (!s->kevent_pool.empty()) {
+    cudaEvent_t e = s->kevent_pool.back();
+    s->kevent_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+// launch the dominant kernel, optionally bracketed by events on the launching stream
+static void launch_step_kernel(rcs_sim* s, const StepArgs& a, uint32_t n_ub, bool sorted_input) {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (s->ktiming) {
+    e0 = kevent_get(s);
+    e1 = kevent_get(s);
+    cudaEventRecord(e0, s->stream);
+  }
+  if (sorted_input && s->opt_step_kernel != 1) {
+    step_warp_kernel<<<blocks_for(n_ub, 32 * SW_WARPS), 32 * SW_WARPS, 0, s->stream>>>(a);
+    // agents with a stencil wider than three columns or very crowded cells (device-side list)
+    step_slow_kernel<<<148 * 4, 128, 0, s->stream>>>(a);
+    s->launches += 2;
+  } else {
+    step_kernel<<<blocks_for(n_ub, 128), 128, 0, s->stream>>>(a);
+    s->launches += 1;
+  }
+  if (s->ktiming) {
+    cudaEventRecord(e1, s->stream);
+    s->kevents.push_back({e0, e1});
+  }
+}
+
+static int drain_kevents(rcs_sim* s) {
+  for (auto& pr : s->kevents) {
+    CU_TRY(s, cudaEventSynchronize(pr.second));
+    float ms = 0.f;
+    CU_TRY(s, cudaEventElapsedTime(&ms, pr.first, pr.second));
+    s->ktime_ms += ms;
+    s->ktime_n += 1;
+    s->kevent_pool.push_back(pr.first);
+    s->kevent_pool.push_back(pr.second);
+  }
+  s->kevents.clear();
+  return RCS_OK;
+}
+
+// Undo a failed step on a strip: the snapshot in `cur` (sorted, ghosts included) is reduced to the agents
+// this rank owns.
+static int rollback_owned(rcs_sim* s, uint32_t n_tot) {
+  role_keep_kernel<<<blocks_for(n_tot, 256), 256, 0, s->stream>>>(n_tot, s->cnt + CNT_TOT, s->srt_cell,
+                                                                  (uint32_t)s->grid.nx, s->strip, s->cellid);
+  s->launches += 1;
+  int rc = exclusive_scan(s, s->cellid, n_tot, s->perm, nullptr);
+  if (rc) return rc;
+  compact_keep_kernel<<<blocks_for(n_tot, 256), 256, 0, s->stream>>>(n_tot, s->cnt + CNT_TOT, s->cellid, s->perm,
+                                                                     s->cur, s->srt, nullptr);
+  s->launches += 1;
+  uint32_t kept = 0;
+  CU_TRY(s, cudaMemcpyAsync(&kept, s->perm + n_tot, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  CU_TRY(s, cudaStreamSynchronize(s->stream));
+  std::swap(s->cur, s->srt);
+  s->n = kept;
+  return RCS_OK;
+}
+
+static int do_sync(rcs_sim* s) {
+  CU_TRY(s, cudaMemcpyAsync(s->h_status, s->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, s->stream));
+  CU_TRY(s, cudaMemcpyAsync(s->h_cnt, s->cnt, CNT_N * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  unsigned long long steps_done = 0;
+  CU_TRY(s, cudaMemcpyAsync(&steps_done, s->d_steps_done, sizeof(steps_done), cudaMemcpyDeviceToHost, s->stream));
+  unsigned long long next_id = s->last_alloc_agent_id;
+  if (s->ever_had_sources)
+    CU_TRY(s, cudaMemcpyAsync(&next_id, s->d_next_id, sizeof(next_id), cudaMemcpyDeviceToHost, s->stream));
+  CU_TRY(s, cudaStreamSynchronize(s->stream));
+  const DevStatus& st = *s->h_status;
+  if (!s->cnt_dirty && !s->pending.empty()) s->n = s->h_cnt[CNT_CUR];
+  if (next_id > s->last_alloc_agent_id) {  // source sinks allocated ids on the device (lib.rs:128-129)
+    s->last_alloc_agent_id = next_id;
+    s->max_id_plus1 = std::max<uint64_t>(s->max_id_plus1, next_id);
+  }
+  s->n_ub = s->n;
+  s->stats.oob_count = st.oob_count;
+  s->stats.first_oob_id = st.first_oob_id;
+  s->stats.nonfinite_count = st.nonfinite_count;
+  s->stats.finite_tti_count = st.finite_tti;
+  s->stats.neighbour_total = st.neighbour_total;
+  s->stats.candidate_total = st.candidate_total;
+  s->stats.spawned = st.spawned;
+  s->stats.destroyed = st.destroyed;
+  s->stats.n_agents = s->n;
+  s->stats.steps = steps_done;
+  int rc = drain_kevents(s);
+  if (rc) return rc;
+  if (st.failed) {
+    // the step with index k (since the last sync) failed; every later one was skipped on the device
+    uint64_t k = steps_done - s->steps_done_at_sync;
+    uint32_t n_snapshot = s->h_cnt[CNT_TOT];
+    if (k < s->pending.size()) {
+      const PendingStep& p = s->pending[k];
+      if (p.snapshot_in_srt) {
+        s->cur = p.srt;
+        s->srt = p.cur;
+      } else {
+        s->cur = p.cur;
+        s->srt = p.srt;
+        n_snapshot = p.n;
+      }
+    }
+    if (st.local_failed && st.oob_count) {
+      s->err = "Index out of bounds";
+      rc = RCS_ERR_OUT_OF_BOUNDS;
+    } else if (st.local_failed && st.capacity_err) {
+      s->err = "capacity exceeded (agents, halo or event buffers)";
+      rc = RCS_ERR_CAPACITY;
+    } else if (st.local_failed && st.halo_err) {
+      s->err = "an agent moved further than the halo ring in one step";
+      rc = RCS_ERR_HALO;
+    } else {
+      s->err = "a neighbouring rank failed its step";
+      rc = RCS_ERR_HALO;
+    }
+    // the snapshot holds the agents that were spawned at the start of the failed step (their events stand);
+    // destroy events of the failed step are dropped
+    s->n = n_snapshot;
+    s->h_cnt[CNT_EV_DESTROY] = s->h_cnt[CNT_EV_DESTROY_SAVE];
+    CU_TRY(s, cudaMemcpyAsync(s->cnt + CNT_EV_DESTROY, s->h_cnt + CNT_EV_DESTROY_SAVE, sizeof(uint32_t),
+                              cudaMemcpyHostToDevice, s->stream));
+    CU_TRY(s, cudaMemsetAsync(&s->d_status->failed, 0, sizeof(unsigned int), s->stream));
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    if (s->strip.enabled && k < s->pending.size() && s->pending[k].snapshot_in_srt) {
+      int rc2 = rollback_owned(s, n_snapshot);
+      if (rc2) return rc2;
+    }
+    s->n_ub = s->n;
+    s->cnt_dirty = true;
+    s->stats.n_agents = s->n;
+    invalidate(s);
+  }
+  s->pending.clear();
+  s->steps_done_at_sync = steps_done;
+  return rc;
+}
+
+static int build_slot_table(rcs_sim* s) {
+  if (s->slot_valid) return RCS_OK;
+  if (s->strip.enabled && s->n) {
+    // agents migrate between ranks: the id range of this handle is whatever currently lives here
+    unsigned long long* d_max = reinterpret_cast<unsigned long long*>(s->d_bad2);
+    CU_TRY(s, cudaMemsetAsync(d_max, 0, sizeof(unsigned long long), s->stream));
+    max_id_kernel<<<blocks_for(s->n, 256), 256, 0, s->stream>>>(s->n, s->cur.id, d_max);
+    s->launches += 1;
+    unsigned long long mx = 0;
+    CU_TRY(s, cudaMemcpyAsync(&mx, d_max, sizeof(mx), cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    s->max_id_plus1 = std::max<uint64_t>(s->max_id_plus1, mx + 1);
+  }
+  uint64_t L = std::max<uint64_t>(s->max_id_plus1, 1);
+  if (L > s->slot_table_cap) {
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    cudaFree(s->slot_of_id); cudaFree(s->id_rank); cudaFree(s->presence);
+    s->slot_of_id = s->id_rank = s->presence = nullptr;
+    uint64_t cap = L + L / 2 + 1024;
+    CU_TRY(s, dalloc(&s->slot_of_id, cap));
+    CU_TRY(s, dalloc(&s->id_rank, cap + 1));
+    CU_TRY(s, dalloc(&s->presence, cap + 16));
+    s->slot_table_cap = cap;
+  }
+  CU_TRY(s, cudaMemsetAsync(s->slot_of_id, 0xff, L * sizeof(uint32_t), s->stream));
+  if (s->n)
+    build_slot_of_id_kernel<<<blocks_for(s->n, 256), 256, 0, s->stream>>>(s->n, s->cur.id, s->slot_of_id, L);
+  presence_kernel<<<blocks_for(L, 256), 256, 0, s->stream>>>(L, s->slot_of_id, s->presence);
+  s->launches += 2;
+  int rc = exclusive_scan(s, s->presence, L, s->id_rank, nullptr);
+  if (rc) return rc;
+  order_by_id_kernel<<<blocks_for(L, 256), 256, 0, s->stream>>>(L, s->slot_of_id, s->id_rank, s->order_by_id);
+  s->launches += 1;
+  CU_TRY(s, cudaGetLastError());
+  s->slot_valid = true;
+  return RCS_OK;
+}
+
+template <class T>
+static int read_array(rcs_sim* s, const T* src, const uint32_t* order, uint32_t n, T* host_out, uint64_t stage_off) {
+  T* st = reinterpret_cast<T*>(static_cast<char*>(s->stage) + stage_off);
+  gather_kernel<T><<<blocks_for(n, 256), 256, 0, s->stream>>>(n, order, src, st);
+  s->launches += 1;
+  CU_TRY(s, cudaMemcpyAsync(host_out, st, (uint64_t)n * sizeof(T), cudaMemcpyDeviceToHost, s->stream));
+  return RCS_OK;
+}
+
+}  // namespace rcs_host

@@ -1,0 +1,281 @@
+// rcs_host_dist.inl -- spatial strips over several GPUs.
+// Part of rcs.cu (single translation unit).
+//
+// Rank r owns the cell columns [c0, c1) of the x-major LocationHash2D grid.  Every step it sends the agents
+// of its outermost W = h + reach columns to each neighbour (h = ring width, reach = columns a radius query
+// can touch beyond the agent's own column) and receives the neighbours' as ghosts.  Ghosts inside the ring
+// (h columns beyond the boundary) are advanced redundantly -- same inputs, same canonical order, same
+// kernels, hence bit-identical results on both ranks -- so an agent that crosses the boundary is simply
+// kept by the rank that owns its new column and dropped by the other: migration needs no second message.
+// Transports: NCCL point-to-point (one process per GPU), or peer copies between handles that live in one
+// process (tests on a single GPU; no kernel ever waits on another kernel).
+
+#include <dlfcn.h>
+
+namespace rcs_host {
+
+static NcclApi g_nccl;
+
+static bool nccl_load(std::string& err) {
+  if (g_nccl.lib) return true;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) {
+    err = std::string("cannot load NCCL: ") + dlerror();
+    return false;
+  }
+  NcclApi a;
+  a.lib = h;
+  a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+  a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+  a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+  a.Send = reinterpret_cast<decltype(a.Send)>(dlsym(h, "ncclSend"));
+  a.Recv = reinterpret_cast<decltype(a.Recv)>(dlsym(h, "ncclRecv"));
+  a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(dlsym(h, "ncclGroupStart"));
+  a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(dlsym(h, "ncclGroupEnd"));
+  a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+  if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.Send || !a.Recv || !a.GroupStart || !a.GroupEnd) {
+    err = "libnccl.so.2 lacks a required entry point";
+    return false;
+  }
+  g_nccl = a;
+  return true;
+}
+
+#define NCCL_TRY(sim, call)                                                                            \
+  do {                                                                                                 \
+    int r__ = (call);                                                                                  \
+    if (r__ != 0) {                                                                                    \
+      (sim)->err = std::string("NCCL error: ") +                                                       \
+                   (g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "?") + " at " #call;         \
+      return RCS_ERR_NCCL;                                                                             \
+    }                                                                                                  \
+  } while (0)
+
+static int halo_alloc(rcs_sim* s, HaloMem& m, uint32_t cap) {
+  const uint64_t bytes = 64 + 8ull * 8ull * cap;
+  CU_TRY(s, cudaMalloc(&m.base, bytes));
+  CU_TRY(s, cudaMemset(m.base, 0, 64));
+  m.bytes = bytes;
+  char* p = static_cast<char*>(m.base);
+  HaloBuf& b = m.buf;
+  b.count = reinterpret_cast<uint32_t*>(p);
+  double* arr = reinterpret_cast<double*>(p + 64);
+  b.x = arr;
+  b.y = arr + (uint64_t)cap;
+  b.vx = arr + 2ull * cap;
+  b.vy = arr + 3ull * cap;
+  b.id = reinterpret_cast<unsigned long long*>(arr + 4ull * cap);
+  b.meta = reinterpret_cast<unsigned long long*>(arr + 5ull * cap);
+  b.pvx = arr + 6ull * cap;
+  b.pvy = arr + 7ull * cap;
+  b.cap = cap;
+  return RCS_OK;
+}
+
+static void halo_free(HaloMem& m) {
+  cudaFree(m.base);
+  m = HaloMem{};
+}
+
+// columns of the grid that can hold an agent: x_idx in [0, x_max]
+static uint64_t strip_columns(const rcs_sim* s) { return s->grid.x_max < 0 ? 0 : (uint64_t)s->grid.x_max + 1; }
+
+static void strip_range(const rcs_sim* s, int rank, int world, uint64_t& c0, uint64_t& c1) {
+  const uint64_t cols = strip_columns(s);
+  c0 = cols * (uint64_t)rank / (uint64_t)world;
+  c1 = cols * (uint64_t)(rank + 1) / (uint64_t)world;
+}
+
+static int strip_setup(rcs_sim* s, int rank, int world, uint64_t halo_capacity) {
+  if (world <= 0 || rank < 0 || rank >= world) {
+    s->err = "bad rank / world";
+    return RCS_ERR_ARG;
+  }
+  if (s->strip.enabled) {
+    s->err = "strips are already initialised on this handle";
+    return RCS_ERR_ARG;
+  }
+  if (s->n != 0 || s->ever_had_sources) {
+    s->err = "rcs_dist_init must come before agents are added; source sinks are not supported on strips";
+    return RCS_ERR_ARG;
+  }
+  const uint64_t ny = s->grid.nx ? s->grid.len / s->grid.nx : 0;
+  if (s->grid.nx == 0 || ny > s->grid.nx) {
+    // with n_y > n_x the reference's width-stride index aliases columns (location_hash_2d.rs:59)
+    s->err = "strips need a grid with n_y <= n_x";
+    return RCS_ERR_ARG;
+  }
+  uint64_t c0, c1, t0, t1;
+  strip_range(s, rank, world, c0, c1);
+  if (c1 <= c0) {
+    s->err = "more ranks than cell columns";
+    return RCS_ERR_ARG;
+  }
+  StripDev st{};
+  st.enabled = 1;
+  st.c0 = (uint32_t)c0;
+  st.c1 = (uint32_t)c1;
+  st.h = 1;
+  strip_range(s, std::max(rank - 1, 0), world, t0, t1);
+  st.lc0 = rank > 0 ? (uint32_t)t0 : (uint32_t)c0;
+  strip_range(s, std::min(rank + 1, world - 1), world, t0, t1);
+  st.rc1 = rank + 1 < world ? (uint32_t)t1 : (uint32_t)c1;
+  uint64_t hc = halo_capacity ? halo_capacity : std::max<uint64_t>(s->cap / 8, 1024);
+  hc = std::min<uint64_t>(hc, s->cap);
+  for (HaloMem* m : {&s->send_l, &s->send_r, &s->recv_l, &s->recv_r}) {
+    int rc = halo_alloc(s, *m, (uint32_t)hc);
+    if (rc) return rc;
+  }
+  CU_TRY(s, dalloc(&s->srt_cell, s->cap + 16));
+  if (!s->cur.pvx) {
+    // ghosts carry the host-planner preferred velocity only when such a planner exists; the halo buffers
+    // always have room for it
+  }
+  s->strip = st;
+  s->rank = rank;
+  s->world = world;
+  s->n_ub = (uint32_t)s->cap;
+  return RCS_OK;
+}
+
+// W = h + reach, from the groups registered so far (reach: see the header comment of this file)
+static int strip_halo_width(rcs_sim* s) {
+  uint64_t reach = 1;
+  for (const GroupDev& g : s->groups) {
+    if (g.lp_kind != LP_ZANLUNGO) continue;
+    double r = g.eyesight / s->grid.res;
+    if (!(r >= 0.0) || r > 1e6) {
+      s->err = "eyesight range too large for strips";
+      return RCS_ERR_HALO;
+    }
+    reach = std::max<uint64_t>(reach, (uint64_t)std::floor(r) + 1);
+  }
+  const uint64_t w = s->strip.h + reach;
+  if (s->world > 1 && w > (uint64_t)(s->strip.c1 - s->strip.c0)) {
+    s->err = "strip narrower than the halo (fewer ranks or a larger cell size needed)";
+    return RCS_ERR_HALO;
+  }
+  s->halo_width = (uint32_t)w;
+  return RCS_OK;
+}
+
+static int step_exchange_nccl(rcs_sim* s) {
+  if (s->world == 1) return RCS_OK;
+  if (!s->nccl_comm) {
+    s->err = "strip handle has no communicator";
+    return RCS_ERR_NCCL;
+  }
+  const int has_l = s->rank > 0, has_r = s->rank + 1 < s->world;
+  NCCL_TRY(s, g_nccl.GroupStart());
+  if (has_l) {
+    NCCL_TRY(s, g_nccl.Send(s->send_l.base, s->send_l.bytes, /*ncclUint8*/ 1, s->rank - 1, s->nccl_comm, s->stream));
+    NCCL_TRY(s, g_nccl.Recv(s->recv_l.base, s->recv_l.bytes, 1, s->rank - 1, s->nccl_comm, s->stream));
+  }
+  if (has_r) {
+    NCCL_TRY(s, g_nccl.Send(s->send_r.base, s->send_r.bytes, 1, s->rank + 1, s->nccl_comm, s->stream));
+    NCCL_TRY(s, g_nccl.Recv(s->recv_r.base, s->recv_r.bytes, 1, s->rank + 1, s->nccl_comm, s->stream));
+  }
+  NCCL_TRY(s, g_nccl.GroupEnd());
+  return RCS_OK;
+}
+
+}  // namespace rcs_host
+
+static void dist_teardown(rcs_sim* s) {
+  using namespace rcs_host;
+  if (s->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->nccl_comm);
+  s->nccl_comm = nullptr;
+  halo_free(s->send_l);
+  halo_free(s->send_r);
+  halo_free(s->recv_l);
+  halo_free(s->recv_r);
+  if (s->ev_packed) cudaEventDestroy(s->ev_packed);
+  if (s->ev_copied) cudaEventDestroy(s->ev_copied);
+  s->ev_packed = s->ev_copied = nullptr;
+  // unlink from a single-process group: the other handles must not touch this one any more
+  for (rcs_sim* o : s->local_group)
+    if (o && o != s)
+      for (rcs_sim*& q : o->local_group)
+        if (q == s) q = nullptr;
+  s->local_group.clear();
+}
+
+extern "C" {
+
+int rcs_nccl_unique_id(uint8_t out_id[128]) {
+  if (!out_id) return RCS_ERR_ARG;
+  if (!nccl_load(g_create_error)) return RCS_ERR_NCCL;
+  Id128 id;
+  int r = g_nccl.GetUniqueId(&id);
+  if (r != 0) {
+    g_create_error = std::string("NCCL error: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    return RCS_ERR_NCCL;
+  }
+  std::memcpy(out_id, id.internal, 128);
+  return RCS_OK;
+}
+
+int rcs_dist_init(rcs_sim* s, int32_t rank, int32_t world, const uint8_t nccl_id[128], uint64_t halo_capacity) {
+  if (!s || (world > 1 && !nccl_id)) return RCS_ERR_ARG;
+  CU_TRY(s, cudaSetDevice(s->device));
+  int rc = do_sync(s);
+  if (rc) return rc;
+  if (world > 1) {
+    if (!nccl_load(s->err)) return RCS_ERR_NCCL;
+    Id128 id;
+    std::memcpy(id.internal, nccl_id, 128);
+    NCCL_TRY(s, g_nccl.CommInitRank(&s->nccl_comm, world, id, rank));
+  }
+  return strip_setup(s, rank, world, halo_capacity);
+}
+
+int rcs_dist_init_local(rcs_sim** sims, int32_t world, uint64_t halo_capacity) {
+  if (!sims || world <= 0) return RCS_ERR_ARG;
+  for (int r = 0; r < world; ++r)
+    if (!sims[r]) return RCS_ERR_ARG;
+  for (int r = 0; r < world; ++r) {
+    rcs_sim* s = sims[r];
+    CU_TRY(s, cudaSetDevice(s->device));
+    int rc = do_sync(s);
+    if (rc) return rc;
+    rc = strip_setup(s, r, world, halo_capacity);
+    if (rc) return rc;
+    CU_TRY(s, cudaEventCreateWithFlags(&s->ev_packed, cudaEventDisableTiming));
+    CU_TRY(s, cudaEventCreateWithFlags(&s->ev_copied, cudaEventDisableTiming));
+    s->local_group.assign(sims, sims + world);
+  }
+  return RCS_OK;
+}
+
+int rcs_dist_step_local(rcs_sim** sims, int32_t world, uint64_t secs, uint32_t nanos, uint32_t flags) {
+  if (!sims || world <= 0) return RCS_ERR_ARG;
+  const double dt = (double)secs + (double)nanos / 1000000000.0;
+  for (int r = 0; r < world; ++r) {
+    rcs_sim* s = sims[r];
+    if (!s || (int)s->local_group.size() != world || s->local_group[r] != s) return RCS_ERR_ARG;
+  }
+  for (int r = 0; r < world; ++r) {
+    rcs_sim* s = sims[r];
+    CU_TRY(s, cudaSetDevice(s->device));
+    int rc = step_phase_a(s, dt);
+    if (rc) return rc;
+  }
+  for (int r = 0; r < world; ++r) {
+    rcs_sim* s = sims[r];
+    CU_TRY(s, cudaSetDevice(s->device));
+    int rc = step_exchange_local(s);
+    if (rc) return rc;
+    rc = step_phase_b(s, dt, flags);
+    if (rc) return rc;
+  }
+  return RCS_OK;
+}
+
+int rcs_dist_strip(rcs_sim* s, int32_t rank, int32_t world, uint64_t* c0, uint64_t* c1) {
+  if (!s || !c0 || !c1 || world <= 0 || rank < 0 || rank >= world) return RCS_ERR_ARG;
+  strip_range(s, rank, world, *c0, *c1);
+  return RCS_OK;
+}
+
+}  // extern "C"

@@ -17,11 +17,42 @@ struct DevStatus {
   unsigned int oob_count;
   unsigned int nonfinite_count;
   unsigned int big_cells;       // cells with more agents than SORT_LOCAL_MAX (handled by the slow sorter)
-  unsigned int failed;          // sticky: a previous async step failed -> later steps are skipped
+  unsigned int failed;          // sticky: a previous async step failed (on ANY rank) -> later steps are skipped
+  unsigned int local_failed;    // this rank's own verdict for the current step (input of the consensus)
+  unsigned int halo_err;        // strips: an owned agent moved further than the halo in one step
+  unsigned int capacity_err;    // spawn / ghost append / event buffers ran out of room
+  unsigned int spawned;         // agents spawned by source sinks in this step
+  unsigned int destroyed;       // agents removed at sinks in this step
+  unsigned int slow_count;      // agents handed to the sequential kernel by the warp-cooperative kernel
   unsigned long long first_oob_id;
   unsigned long long finite_tti;
   unsigned long long neighbour_total;
   unsigned long long candidate_total;
+};
+
+// device-side agent counts (the host only knows upper bounds while steps with churn are in flight)
+enum : int { CNT_CUR = 0, CNT_TOT = 1, CNT_SAVE = 2, CNT_EV_SPAWN = 3, CNT_EV_DESTROY = 4, CNT_EV_SPAWN_SAVE = 5,
+             CNT_EV_DESTROY_SAVE = 6, CNT_N = 8 };
+
+// one source sink on the device (source_sink.rs:36-60 + the per-step logic of lib.rs:199-254, 305-336)
+struct SourceSinkDev {
+  double sx, sy;            // source
+  double rate;              // MonotonicCrowd::rate (source_sink.rs:85-100)
+  double thr2_sink;         // smallest double T with sqrt(T) >= radius_sink
+  long long pl, pr, pb, pt; // get_bounds(0.4, source): stencil of the spawn probe (lib.rs:212-214)
+  uint32_t wp_off, n_wp;    // waypoints in the shared waypoint table
+  uint32_t grp;             // group of the agents it spawns
+  uint32_t loop_forever;
+  uint32_t alive;           // 0 after remove_source_sink
+  uint32_t pad_;
+};
+
+// spatial strips: this rank owns cell columns [c0, c1); h = halo ring width
+struct StripDev {
+  uint32_t enabled;
+  uint32_t c0, c1, h;   // own columns [c0, c1); ring width h (columns advanced redundantly on both sides)
+  uint32_t lc0, rc1;    // the left neighbour owns [lc0, c0), the right one [c1, rc1)
+  uint32_t pad_[2];
 };
 
 struct AgentArrays {
@@ -40,12 +71,14 @@ constexpr uint32_t CELL_DEAD = 0xffffffffu;
 // ---------------------------------------------------------------------------------------------
 // A1/A2: cell of every agent (LocationHash2D::location_to_index) + histogram.
 // ---------------------------------------------------------------------------------------------
-__global__ void bin_count_kernel(GridDev g, uint32_t n, const double* __restrict__ x, const double* __restrict__ y,
-                                 uint32_t* __restrict__ cellid, uint32_t* __restrict__ cell_count,
-                                 DevStatus* status) {
+// Agents [*first (0 if null), min(n_ub, *last)) of the unsorted arrays.
+__global__ void bin_count_kernel(GridDev g, uint32_t n_ub, const uint32_t* __restrict__ first,
+                                 const uint32_t* __restrict__ last, const double* __restrict__ x,
+                                 const double* __restrict__ y, uint32_t* __restrict__ cellid,
+                                 uint32_t* __restrict__ cell_count, DevStatus* status) {
   if (status->failed) return;
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x + (first ? *first : 0u);
+  if (i >= n_ub || i >= *last) return;
   uint64_t idx;
   if (location_to_index(g, x[i], y[i], idx)) {
     cellid[i] = (uint32_t)idx;
@@ -183,11 +216,12 @@ __global__ void scan_apply_kernel(const uint32_t* __restrict__ in, uint64_t len,
 // ---------------------------------------------------------------------------------------------
 // A2: counting-sort scatter of a permutation (slot order inside a cell is fixed by the next kernel)
 // ---------------------------------------------------------------------------------------------
-__global__ void scatter_perm_kernel(uint32_t n, const uint32_t* __restrict__ cellid, uint32_t* __restrict__ cursor,
+__global__ void scatter_perm_kernel(uint32_t n_ub, const uint32_t* __restrict__ n_ptr,
+                                    const uint32_t* __restrict__ cellid, uint32_t* __restrict__ cursor,
                                     uint32_t* __restrict__ perm, const DevStatus* status) {
   if (status->failed) return;
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= n_ub || i >= *n_ptr) return;
   uint32_t c = cellid[i];
   if (c == CELL_DEAD) return;
   uint32_t pos = atomicAdd(&cursor[c], 1u);
@@ -259,12 +293,14 @@ __global__ void sort_big_cells_kernel(const uint32_t* __restrict__ cell_start, c
 
 // Physical reorder into canonical order: sorted[k] = cur[perm[k]].
 __global__ void gather_sorted_kernel(uint32_t n, const uint32_t* __restrict__ perm, AgentArrays cur,
-                                     AgentArrays srt, const uint32_t* __restrict__ n_sorted,
+                                     AgentArrays srt, const uint32_t* __restrict__ cellid,
+                                     uint32_t* __restrict__ srt_cell, const uint32_t* __restrict__ n_sorted,
                                      const DevStatus* status) {
   if (status->failed) return;
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n || k >= *n_sorted) return;
   uint32_t i = perm[k];
+  if (srt_cell) srt_cell[k] = cellid[i];
   srt.x[k] = cur.x[i];
   srt.y[k] = cur.y[i];
   srt.vx[k] = cur.vx[i];
@@ -290,11 +326,40 @@ struct StepArgs {
   const GroupDev* groups;
   double dt;                  // Duration::as_secs_f64 (lib.rs:295)
   double *ox, *oy, *ovx, *ovy;  // new state, same order
+  uint64_t* oid;              // id / group / waypoint / host preferred velocity of the new state
+  uint32_t *ogrp, *owp;       //   (all nullptr on the streaming path, which updates x,y,vx,vy in place)
+  double *opvx, *opvy;
   double *t_i, *fx, *fy;      // optional trace outputs (nullptr when tracing is off)
   uint32_t* nb_count;         // optional: neighbour count per agent (trace)
+  uint64_t* tr_id;            // optional: id of the agent in each trace slot
+  uint32_t* tr_own;           // optional: 1 if the slot holds an agent this rank owns and advanced
   DevStatus* status;
   uint32_t collect_stats;
+  uint32_t no_commit;         // RCS_STEP_NO_COMMIT: keep flags select the owned pre-step agents
+  const unsigned long long* steps_done;  // device step counter (stamps destroy events)
+  // churn: agents that leave (sink reached, lib.rs:318-323; strip ownership) get keep = 0
+  uint32_t* keep;                  // nullptr when nothing can leave
+  const uint32_t* cell;            // insert cell of every sorted agent (strips)
+  StripDev strip;
+  const SourceSinkDev* ss;         // nullptr when there are no source sinks
+  const double* ss_wp;             // waypoint table, interleaved x,y
+  uint32_t* cnt;                   // device counters (CNT_*)
+  unsigned long long* ev_destroyed;  // (id, step) pairs of agents removed at sinks
+  uint32_t ev_cap;
+  uint32_t* slow_list;             // warp kernel: agents left to the sequential kernel
 };
+
+enum : uint32_t { ROLE_PASSIVE = 0, ROLE_OWN = 1, ROLE_RING = 2 };
+
+// Strips: an agent is advanced by the rank that owns its column AND, redundantly and bit-identically,
+// by the neighbour rank that holds it in the inner halo ring (so migration needs no message).
+__device__ __forceinline__ uint32_t agent_role(const StepArgs& a, uint32_t i) {
+  if (!a.strip.enabled) return ROLE_OWN;
+  const uint32_t cx = a.cell[i] / (uint32_t)a.grid.nx;
+  if (cx >= a.strip.c0 && cx < a.strip.c1) return ROLE_OWN;
+  if (cx + a.strip.h >= a.strip.c0 && cx < a.strip.c1 + a.strip.h) return ROLE_RING;
+  return ROLE_PASSIVE;
+}
 
 struct Self {
   double px, py, vx, vy, pfx, pfy;
@@ -410,27 +475,90 @@ __device__ __forceinline__ void high_level_velocity(const StepArgs& a, uint32_t 
   }
 }
 
-// Explicit Euler + commit outputs + error accounting (lib.rs:295-302) for one agent.
-__device__ __forceinline__ void integrate_and_store(const StepArgs& a, uint32_t i, const Self& me, double velx,
-                                                    double vely, double t_i, double fx, double fy, uint32_t nbc) {
+// Explicit Euler + commit outputs + error accounting (lib.rs:295-302), then the waypoint / sink test on
+// the OLD position (lib.rs:305-336) and, for strips, the ownership decision by the NEW position.
+__device__ __forceinline__ void integrate_and_store(const StepArgs& a, uint32_t i, const Self& me, const GroupDev& g,
+                                                    uint32_t grp, uint32_t role, double velx, double vely, double t_i,
+                                                    double fx, double fy, uint32_t nbc) {
   const double nx = me.px + velx * a.dt;
   const double ny = me.py + vely * a.dt;
   a.ox[i] = nx;
   a.oy[i] = ny;
   a.ovx[i] = velx;
   a.ovy[i] = vely;
+  const bool own = role == ROLE_OWN;
   if (a.t_i) {
     a.t_i[i] = t_i;
     a.fx[i] = fx;
     a.fy[i] = fy;
     a.nb_count[i] = nbc;
+    a.tr_id[i] = me.id;
+    a.tr_own[i] = own ? 1u : 0u;
   }
-  uint64_t idx;
-  if (!location_to_index(a.grid, nx, ny, idx)) {  // add_or_update(new_pos) error path, lib.rs:299-302
+  // add_or_update(new_pos) error path, lib.rs:299-302
+  const uint64_t x_idx = f64_as_usize((nx - a.grid.offx) / a.grid.res);
+  const uint64_t y_idx = f64_as_usize((ny - a.grid.offy) / a.grid.res);
+  const uint64_t idx = x_idx * a.grid.nx + y_idx;
+  const bool inb = idx < a.grid.len;
+  if (!inb && own) {
     atomicAdd(&a.status->oob_count, 1u);
     atomicMin(&a.status->first_oob_id, (unsigned long long)me.id);
   }
-  if (!(isfinite(nx) && isfinite(ny) && isfinite(velx) && isfinite(vely))) atomicAdd(&a.status->nonfinite_count, 1u);
+  if (own && !(isfinite(nx) && isfinite(ny) && isfinite(velx) && isfinite(vely)))
+    atomicAdd(&a.status->nonfinite_count, 1u);
+  if (!a.oid) return;  // streaming path: x,y,vx,vy only
+  uint32_t wp = a.in.wp[i];
+  bool keep = true;
+  if (a.ss && g.source_sink >= 0) {
+    const SourceSinkDev& ss = a.ss[g.source_sink];
+    if (ss.alive && wp < ss.n_wp) {
+      const double ddx = me.px - a.ss_wp[2 * (ss.wp_off + wp)];
+      const double ddy = me.py - a.ss_wp[2 * (ss.wp_off + wp) + 1];
+      if (ddx * ddx + ddy * ddy < ss.thr2_sink) {  // (position - waypoint).norm() < radius_sink, lib.rs:314
+        if (wp == ss.n_wp - 1) {
+          if (ss.loop_forever) {
+            wp = 0;
+          } else {
+            keep = false;  // to_be_removed: still moved and committed this step, removed after (lib.rs:378)
+            if (own && !a.no_commit) {
+              const uint32_t k = atomicAdd(&a.cnt[CNT_EV_DESTROY], 1u);
+              if (k < a.ev_cap) {
+                a.ev_destroyed[2 * k] = me.id;
+                a.ev_destroyed[2 * k + 1] = *a.steps_done;
+              } else {
+                atomicAdd(&a.status->capacity_err, 1u);
+              }
+              atomicAdd(&a.status->destroyed, 1u);
+            }
+          }
+        } else {
+          wp += 1;
+        }
+      }
+    }
+  }
+  a.oid[i] = me.id;
+  a.ogrp[i] = grp;
+  a.owp[i] = wp;
+  if (a.opvx) {
+    a.opvx[i] = a.in.pvx[i];
+    a.opvy[i] = a.in.pvy[i];
+  }
+  if (a.strip.enabled) {
+    // The agent stays with the rank that owns its NEW column.  Every agent that leaves a strip must have
+    // been in the neighbour's ring (old column within h of the boundary) and must land inside the
+    // neighbour's strip; otherwise no rank would keep it.
+    const uint32_t ocx = a.cell[i] / (uint32_t)a.grid.nx;
+    const bool mine = inb && x_idx >= a.strip.c0 && x_idx < a.strip.c1;
+    if (own && inb && !mine) {
+      const bool ok = x_idx < a.strip.c0 ? (ocx < a.strip.c0 + a.strip.h && x_idx >= a.strip.lc0)
+                                         : (ocx + a.strip.h >= a.strip.c1 && x_idx < a.strip.rc1);
+      if (!ok) atomicAdd(&a.status->halo_err, 1u);
+    }
+    keep = keep && mine;
+  }
+  if (a.no_commit) keep = own;  // the pre-step snapshot stays: this rank keeps exactly what it owned
+  if (a.keep) a.keep[i] = keep ? 1u : 0u;
 }
 
 __device__ __forceinline__ void warp_stats(const StepArgs& a, uint32_t cand, uint32_t nbc, uint32_t finite) {
@@ -449,32 +577,59 @@ __device__ __forceinline__ void warp_stats(const StepArgs& a, uint32_t cand, uin
   }
 }
 
+// One agent, sequentially: high-level velocity, Zanlungo, Euler.  Body of the thread-per-agent kernel
+// and of the kernel that finishes the agents the warp-cooperative kernel left aside.
+__device__ __forceinline__ void step_one_agent(const StepArgs& a, uint32_t i, uint32_t& cand, uint32_t& nbc,
+                                               uint32_t& finite) {
+  const uint32_t role = agent_role(a, i);
+  if (role == ROLE_PASSIVE) {
+    if (a.keep) a.keep[i] = 0u;
+    return;
+  }
+  const GroupDev& g = a.groups[a.in.grp[i]];
+  Self me;
+  me.px = a.in.x[i];
+  me.py = a.in.y[i];
+  me.vx = a.in.vx[i];
+  me.vy = a.in.vy[i];
+  me.id = a.in.id[i];
+  double velx, vely;
+  high_level_velocity(a, i, g, me, velx, vely);
+  double t_i = RCS_INF, fx = 0.0, fy = 0.0;
+  uint32_t c = 0, nb = 0;
+  if (g.lp_kind == LP_ZANLUNGO) {
+    zanlungo_sequential(a, i, me, g, t_i, fx, fy, nb, c);
+    // zanlungo.rs:216
+    velx = velx + fx * g.inv_mass;
+    vely = vely + fy * g.inv_mass;
+  }
+  integrate_and_store(a, i, me, g, a.in.grp[i], role, velx, vely, t_i, fx, fy, nb);
+  if (role == ROLE_OWN) {  // statistics are per owned agent so that they add up over ranks
+    cand += c;
+    nbc += nb;
+    finite += (g.lp_kind == LP_ZANLUNGO && t_i != RCS_INF) ? 1u : 0u;
+  }
+}
+
 // Thread-per-agent form of the hot kernel (also the streaming kernel of NoLocalPlan-only crowds).
 __global__ void __launch_bounds__(128) step_kernel(StepArgs a) {
   if (a.status->failed) return;
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t n_live = *a.n_sorted;
   uint32_t cand = 0, nbc = 0, finite = 0;
-  if (i < a.n && i < n_live) {
-    const GroupDev& g = a.groups[a.in.grp[i]];
-    Self me;
-    me.px = a.in.x[i];
-    me.py = a.in.y[i];
-    me.vx = a.in.vx[i];
-    me.vy = a.in.vy[i];
-    me.id = a.in.id[i];
-    double velx, vely;
-    high_level_velocity(a, i, g, me, velx, vely);
-    double t_i = RCS_INF, fx = 0.0, fy = 0.0;
-    if (g.lp_kind == LP_ZANLUNGO) {
-      zanlungo_sequential(a, i, me, g, t_i, fx, fy, nbc, cand);
-      finite = t_i != RCS_INF ? 1u : 0u;
-      // zanlungo.rs:216
-      velx = velx + fx * g.inv_mass;
-      vely = vely + fy * g.inv_mass;
-    }
-    integrate_and_store(a, i, me, velx, vely, t_i, fx, fy, nbc);
-  }
+  if (i < a.n && i < n_live) step_one_agent(a, i, cand, nbc, finite);
+  else if (a.keep && i < a.n) a.keep[i] = 0u;
+  warp_stats(a, cand, nbc, finite);
+}
+
+// Finishes the agents the warp-cooperative kernel put on the slow list (stencil wider than three
+// columns or more than SW_MAXC candidates).  Grid-stride over the device-side count.
+__global__ void __launch_bounds__(128) step_slow_kernel(StepArgs a) {
+  if (a.status->failed) return;
+  const uint32_t n_slow = a.status->slow_count;
+  uint32_t cand = 0, nbc = 0, finite = 0;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_slow; k += gridDim.x * blockDim.x)
+    step_one_agent(a, a.slow_list[k], cand, nbc, finite);
   warp_stats(a, cand, nbc, finite);
 }
 
@@ -483,6 +638,7 @@ __global__ void trace_neighbours_kernel(StepArgs a, const uint32_t* __restrict__
                                         uint64_t* __restrict__ nb_ids) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n || i >= *a.n_sorted) return;
+  if (agent_role(a, i) == ROLE_PASSIVE) return;  // never advanced: no list (its nb_count stays 0)
   const GroupDev& g = a.groups[a.in.grp[i]];
   if (g.lp_kind != LP_ZANLUNGO) return;
   uint32_t o = nb_offsets[i];
@@ -511,6 +667,112 @@ __global__ void query_radius_kernel(GridDev g, const uint32_t* __restrict__ cell
   if (!mode) counts[q] = cnt;
 }
 
+// ---------------------------------------------------------------------------------------------
+// SpatialIndex::get_nearest_neighbours (location_hash_2d.rs:151-238), batched.  The ring walk is the
+// reference's, quirks included: the four side loops are half-open, so cell (x-s, y-s) is visited twice
+// and cell (x+s, y+s) never; the walk stops after the first ring that brings the candidate count to n
+// (not a true kNN); candidates are then STABLY sorted by distance (sort_by + partial_cmp, :226-230).
+// f(c) is called for every valid data cell in visiting order and returns the number of agents in it.
+// ---------------------------------------------------------------------------------------------
+template <class F>
+__device__ __forceinline__ uint64_t knn_walk(const GridDev& g, double px, double py, uint64_t n, F&& f) {
+  const int64_t x_idx = f64_floor_as_i64((px - g.offx) / g.res);  // location_to_xy_signed_idx, :68-72
+  const int64_t y_idx = f64_floor_as_i64((py - g.offy) / g.res);
+  uint64_t have = 0;
+  bool all_oob = false;
+  auto visit = [&](int64_t cx, int64_t cy, uint64_t& oob) {
+    // signed_idx_to_data_idx, :74-85
+    bool ok = cx >= 0 && cy >= 0;
+    uint64_t idx = 0;
+    if (ok) {
+      idx = (uint64_t)cx * g.nx + (uint64_t)cy;
+      ok = idx < g.len;
+    }
+    if (ok) have += f(idx);
+    else oob += 1;
+  };
+  for (int64_t step = 0; have < n && !all_oob; ++step) {
+    uint64_t oob = 0, scanned = 0;
+    if (step == 0) {
+      visit(x_idx, y_idx, oob);
+      scanned = 1;
+    } else {
+      for (int64_t i = x_idx - step; i < x_idx + step; ++i) visit(i, y_idx + step, oob);  // top line
+      for (int64_t i = x_idx - step; i < x_idx + step; ++i) visit(i, y_idx - step, oob);  // bottom line
+      for (int64_t i = y_idx - step; i < y_idx + step; ++i) visit(x_idx - step, i, oob);  // left line
+      for (int64_t i = y_idx - step; i < y_idx + step; ++i) visit(x_idx + step, i, oob);  // right line
+      scanned = (uint64_t)(8 * step);
+    }
+    if (oob == scanned) all_oob = true;
+  }
+  return have;
+}
+
+// pass 0: counts[q] = number of candidates the walk collects (duplicates included)
+__global__ void knn_count_kernel(GridDev g, const uint32_t* __restrict__ cell_start, uint32_t nq,
+                                 const double* __restrict__ qxy, uint64_t k, uint32_t* __restrict__ counts) {
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  uint64_t m = knn_walk(g, qxy[2 * q], qxy[2 * q + 1], k,
+                        [&](uint64_t c) { return (uint64_t)(cell_start[c + 1] - cell_start[c]); });
+  counts[q] = (uint32_t)m;
+}
+
+// pass 1: candidate slots and distances in visiting order (ascending id inside a cell)
+__global__ void knn_fill_kernel(GridDev g, const uint32_t* __restrict__ cell_start, const double* __restrict__ xs,
+                                const double* __restrict__ ys, uint32_t nq, const double* __restrict__ qxy, uint64_t k,
+                                const uint32_t* __restrict__ offsets, uint32_t* __restrict__ cand_slot,
+                                double* __restrict__ cand_dist) {
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const double px = qxy[2 * q], py = qxy[2 * q + 1];
+  uint32_t o = offsets[q];
+  knn_walk(g, px, py, k, [&](uint64_t c) {
+    const uint32_t s = cell_start[c], e = cell_start[c + 1];
+    for (uint32_t j = s; j < e; ++j) {
+      const double dx = xs[j] - px, dy = ys[j] - py;
+      cand_slot[o] = j;
+      cand_dist[o] = sqrt(dx * dx + dy * dy);  // (a_pos - position).norm(), :227
+      ++o;
+    }
+    return (uint64_t)(e - s);
+  });
+}
+
+// pass 2: one warp per query; stable rank by distance, the first min(k, m) go out
+__global__ void knn_select_kernel(uint32_t nq, uint64_t k, const uint32_t* __restrict__ offsets,
+                                  const uint32_t* __restrict__ cand_slot, const double* __restrict__ cand_dist,
+                                  const uint64_t* __restrict__ ids, uint64_t* __restrict__ out_ids,
+                                  uint64_t* __restrict__ out_counts) {
+  const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  if (q >= nq) return;
+  const uint32_t s = offsets[q], m = offsets[q + 1] - s;
+  for (uint32_t t = lane; t < m; t += 32) {
+    const double d = cand_dist[s + t];
+    uint32_t rank = 0;
+    for (uint32_t u = 0; u < m; ++u) {
+      const double du = cand_dist[s + u];
+      rank += (du < d || (u < t && !(d < du))) ? 1u : 0u;  // stable: earlier equal elements stay first
+    }
+    if (rank < k) out_ids[(uint64_t)q * k + rank] = ids[cand_slot[s + t]];
+  }
+  if (lane == 0) out_counts[q] = m < k ? m : k;
+}
+
+// keep[i] = 1 for the sorted agents this rank owns (rollback of a failed step on a strip)
+__global__ void role_keep_kernel(uint32_t n_ub, const uint32_t* __restrict__ n_ptr, const uint32_t* __restrict__ cell,
+                                 uint32_t nx, StripDev st, uint32_t* __restrict__ keep) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_ub) return;
+  uint32_t k = 0;
+  if (i < *n_ptr) {
+    const uint32_t cx = cell[i] / nx;
+    k = (cx >= st.c0 && cx < st.c1) ? 1u : 0u;
+  }
+  keep[i] = k;
+}
+
 __global__ void cell_of_kernel(GridDev g, uint32_t n, const double* __restrict__ xy, long long* __restrict__ out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -527,6 +789,18 @@ __global__ void build_slot_of_id_kernel(uint32_t n, const uint64_t* __restrict__
   if (i >= n) return;
   uint64_t v = id[i];
   if (v < table_len) slot_of_id[v] = i;
+}
+
+// largest live id (strips: agents migrate in with ids this handle never allocated)
+__global__ void max_id_kernel(uint32_t n, const uint64_t* __restrict__ id, unsigned long long* out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long v = i < n ? (unsigned long long)id[i] : 0ull;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    unsigned long long o = __shfl_down_sync(0xffffffffu, v, d);
+    v = o > v ? o : v;
+  }
+  if ((threadIdx.x & 31) == 0 && v) atomicMax(out, v);
 }
 
 // presence[v] = 1 if id v is live (input of the rank scan that yields ascending-id order)
@@ -586,9 +860,293 @@ __global__ void fill_f64_kernel(uint64_t n, double* p, double v) {
   if (i < n) p[i] = v;
 }
 
-// marks a step as failed on the device so that later async steps become no-ops (sticky)
-__global__ void finish_step_kernel(DevStatus* status) {
-  if (status->oob_count) status->failed = 1;
+// ---------------------------------------------------------------------------------------------
+// Step bookkeeping on the device.  Steps are enqueued asynchronously; a step that fails makes every
+// later kernel of the handle a no-op (status->failed is sticky until rcs_sync reports it).
+// ---------------------------------------------------------------------------------------------
+__global__ void begin_step_kernel(DevStatus* st, uint32_t* cnt) {
+  if (st->failed) return;
+  st->oob_count = 0;
+  st->nonfinite_count = 0;
+  st->big_cells = 0;
+  st->local_failed = 0;
+  st->halo_err = 0;
+  st->capacity_err = 0;
+  st->spawned = 0;
+  st->destroyed = 0;
+  st->slow_count = 0;
+  st->first_oob_id = ~0ull;
+  st->finite_tti = 0;
+  st->neighbour_total = 0;
+  st->candidate_total = 0;
+  cnt[CNT_SAVE] = cnt[CNT_CUR];
+  cnt[CNT_TOT] = cnt[CNT_CUR];
+  cnt[CNT_EV_SPAWN_SAVE] = cnt[CNT_EV_SPAWN];
+  cnt[CNT_EV_DESTROY_SAVE] = cnt[CNT_EV_DESTROY];
+}
+
+// after the step kernels, before anything is committed: does this step stand?
+__global__ void verdict_kernel(DevStatus* st, int oob_fails) {
+  if (st->failed) return;
+  if ((oob_fails && st->oob_count) || st->halo_err || st->capacity_err) {
+    st->local_failed = 1;
+    st->failed = 1;
+  }
+}
+
+__global__ void end_step_kernel(DevStatus* st, unsigned long long* steps_done) {
+  if (st->failed) return;
+  *steps_done += 1;
+}
+
+__global__ void set_counts_kernel(uint32_t* cnt, uint32_t n) {
+  cnt[CNT_CUR] = n;
+  cnt[CNT_TOT] = n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Churn: stream compaction of the agents whose keep flag is set (despawn at sinks, lib.rs:378-380;
+// strip ownership).  pos = exclusive scan of keep; the new live count is pos[n].
+// ---------------------------------------------------------------------------------------------
+__global__ void compact_keep_kernel(uint32_t n_ub, const uint32_t* __restrict__ n_ptr,
+                                    const uint32_t* __restrict__ keep, const uint32_t* __restrict__ pos,
+                                    AgentArrays in, AgentArrays out, const DevStatus* status) {
+  if (status && status->failed) return;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_ub || i >= *n_ptr || !keep[i]) return;
+  uint32_t k = pos[i];
+  out.x[k] = in.x[i];
+  out.y[k] = in.y[i];
+  out.vx[k] = in.vx[i];
+  out.vy[k] = in.vy[i];
+  out.id[k] = in.id[i];
+  out.grp[k] = in.grp[i];
+  out.wp[k] = in.wp[i];
+  if (in.pvx) {
+    out.pvx[k] = in.pvx[i];
+    out.pvy[k] = in.pvy[i];
+  }
+}
+
+// keep flags beyond the live count must be 0 before the scan
+__global__ void clear_keep_tail_kernel(uint32_t n_ub, const uint32_t* __restrict__ n_ptr, uint32_t* keep) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_ub && i >= *n_ptr) keep[i] = 0u;
+}
+
+__global__ void set_count_kernel(uint32_t* dst, const uint32_t* src, const DevStatus* status) {
+  if (status && status->failed) return;
+  *dst = *src;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Source sinks (lib.rs:199-254).  Spawn probe: `get_neighbours_in_radius(0.4, source)` must be empty.
+// The probe runs over the agents (not over the index): an agent blocks source s iff the reference's
+// query would have returned it, i.e. its INSERT cell is one of the cells of s's query stencil and its
+// distance to the source passes the strict test.  Sources are looked up through a small static grid.
+// ---------------------------------------------------------------------------------------------
+struct SourceGridDev {
+  double x0, y0, cell;        // lower corner and cell size (>= 1 m) of the source lookup grid
+  uint32_t nx, ny;
+  const uint32_t* start;      // nx*ny+1
+  const uint32_t* items;      // source-sink indices
+};
+
+__global__ void ss_probe_kernel(GridDev g, SourceGridDev sg, const SourceSinkDev* __restrict__ ss, double thr2_probe,
+                                uint32_t n_ub, const uint32_t* __restrict__ n_ptr, const double* __restrict__ x,
+                                const double* __restrict__ y, uint32_t* __restrict__ blocked,
+                                const DevStatus* status) {
+  if (status->failed) return;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_ub || i >= *n_ptr) return;
+  const double px = x[i], py = y[i];
+  // conservative range of lookup cells around the agent (0.4 m radius + slack)
+  const double fx0 = floor((px - 0.45 - sg.x0) / sg.cell), fx1 = floor((px + 0.45 - sg.x0) / sg.cell);
+  const double fy0 = floor((py - 0.45 - sg.y0) / sg.cell), fy1 = floor((py + 0.45 - sg.y0) / sg.cell);
+  if (!(fx1 >= 0.0 && fy1 >= 0.0 && fx0 < (double)sg.nx && fy0 < (double)sg.ny)) return;  // also rejects NaN
+  const uint32_t cx0 = fx0 < 0.0 ? 0u : (uint32_t)fx0, cx1 = fx1 >= (double)sg.nx ? sg.nx - 1 : (uint32_t)fx1;
+  const uint32_t cy0 = fy0 < 0.0 ? 0u : (uint32_t)fy0, cy1 = fy1 >= (double)sg.ny ? sg.ny - 1 : (uint32_t)fy1;
+  uint64_t my_cell;
+  if (!location_to_index(g, px, py, my_cell)) return;  // not in the index at all
+  for (uint32_t cx = cx0; cx <= cx1; ++cx) {
+    for (uint32_t cy = cy0; cy <= cy1; ++cy) {
+      const uint32_t c = cx * sg.ny + cy;
+      for (uint32_t k = sg.start[c]; k < sg.start[c + 1]; ++k) {
+        const uint32_t sidx = sg.items[k];
+        const SourceSinkDev& s = ss[sidx];
+        const double dx = px - s.sx, dy = py - s.sy;
+        if (!(dx * dx + dy * dy < thr2_probe)) continue;  // (agent_pos - source).norm() < 0.4
+        // is my insert cell visited by `for x in left..=right { for y in bottom..=top }`?
+        long long xl = s.pl < 0 ? 0 : s.pl, xr = s.pr > g.x_max ? g.x_max : s.pr;
+        bool hit = false;
+        for (long long qx = xl; qx <= xr && !hit; ++qx) {
+          uint64_t c_lo, c_hi;
+          if (column_cell_range(g, qx, s.pb, s.pt, c_lo, c_hi)) hit = my_cell >= c_lo && my_cell <= c_hi;
+        }
+        if (hit) blocked[sidx] = 1u;
+      }
+    }
+  }
+}
+
+// One block.  Sources in ascending id order; at most ONE agent per source per step and only when the
+// generator asks for >= 1 (the reference's loop over spawn_number is commented out, lib.rs:207-219).
+// Ids are allocated sequentially (lib.rs:128-129) in that order.
+__global__ void ss_spawn_kernel(GridDev g, const SourceSinkDev* __restrict__ ss, uint32_t n_ss, double dt,
+                                uint32_t* __restrict__ blocked, AgentArrays cur, uint32_t cap, uint32_t* cnt,
+                                unsigned long long* next_id, unsigned long long* ev_id, double* ev_xy, uint32_t ev_cap,
+                                DevStatus* status) {
+  if (status->failed) return;
+  __shared__ uint32_t base;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  const uint32_t n0 = cnt[CNT_CUR];
+  const unsigned long long id0 = *next_id;
+  const uint32_t ev0 = cnt[CNT_EV_SPAWN];
+  for (uint32_t b = 0; b < n_ss; b += SCAN_THREADS) {
+    const uint32_t k = b + threadIdx.x;
+    uint32_t spawn = 0;
+    if (k < n_ss) {
+      const SourceSinkDev& s = ss[k];
+      const uint64_t want = f64_as_usize(round(dt * s.rate));  // MonotonicCrowd, source_sink.rs:97-100
+      spawn = (s.alive && want > 0 && !blocked[k]) ? 1u : 0u;
+      blocked[k] = 0u;
+    }
+    uint32_t total;
+    const uint32_t rank = block_exclusive_scan(spawn, total);
+    const uint32_t off = base;
+    __syncthreads();
+    if (spawn) {
+      const uint32_t slot = n0 + off + rank;
+      if (slot < cap) {
+        const SourceSinkDev& s = ss[k];
+        cur.x[slot] = s.sx;
+        cur.y[slot] = s.sy;
+        cur.vx[slot] = 0.0;
+        cur.vy[slot] = 0.0;
+        cur.id[slot] = id0 + off + rank;
+        cur.grp[slot] = s.grp;
+        cur.wp[slot] = 0u;
+        if (cur.pvx) {
+          cur.pvx[slot] = __longlong_as_double(0x7ff8000000000000LL);
+          cur.pvy[slot] = __longlong_as_double(0x7ff8000000000000LL);
+        }
+        const uint32_t e = ev0 + off + rank;
+        if (e < ev_cap) {
+          ev_id[e] = id0 + off + rank;
+          ev_xy[2 * e] = s.sx;
+          ev_xy[2 * e + 1] = s.sy;
+        } else {
+          atomicAdd(&status->capacity_err, 1u);
+        }
+      } else {
+        atomicAdd(&status->capacity_err, 1u);
+      }
+    }
+    if (threadIdx.x == 0) base = off + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    uint32_t total = base;
+    if (n0 + total > cap) total = cap - n0;
+    cnt[CNT_CUR] = n0 + total;
+    cnt[CNT_TOT] = n0 + total;
+    cnt[CNT_EV_SPAWN] = (ev0 + total > ev_cap) ? ev_cap : ev0 + total;
+    *next_id = id0 + base;
+    status->spawned = base;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Strips: halo pack / unpack.  A halo buffer is [count u32, pad][x][y][vx][vy][id][meta][pvx][pvy],
+// each array `cap` entries.  Packed order is arbitrary (atomic append); the receiver re-sorts.
+// ---------------------------------------------------------------------------------------------
+struct HaloBuf {
+  uint32_t* count;
+  double *x, *y, *vx, *vy;
+  unsigned long long* id;
+  unsigned long long* meta;  // grp | wp << 32
+  double *pvx, *pvy;
+  uint32_t cap;
+};
+
+__global__ void halo_pack_kernel(uint32_t n_ub, const uint32_t* __restrict__ n_ptr, AgentArrays cur,
+                                 const uint32_t* __restrict__ cellid, uint32_t nx, StripDev st, uint32_t width,
+                                 HaloBuf left, HaloBuf right, int has_left, int has_right, DevStatus* status) {
+  if (status->failed) return;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_ub || i >= *n_ptr) return;
+  const uint32_t c = cellid[i];
+  if (c == CELL_DEAD) return;
+  const uint32_t cx = c / nx;
+  for (int side = 0; side < 2; ++side) {
+    const bool send = side == 0 ? (has_left && cx < st.c0 + width) : (has_right && cx + width >= st.c1);
+    if (!send) continue;
+    HaloBuf& b = side == 0 ? left : right;
+    const uint32_t k = atomicAdd(b.count, 1u);
+    if (k >= b.cap) {
+      atomicAdd(&status->capacity_err, 1u);
+      continue;
+    }
+    b.x[k] = cur.x[i];
+    b.y[k] = cur.y[i];
+    b.vx[k] = cur.vx[i];
+    b.vy[k] = cur.vy[i];
+    b.id[k] = cur.id[i];
+    b.meta[k] = (unsigned long long)cur.grp[i] | ((unsigned long long)cur.wp[i] << 32);
+    if (cur.pvx) {
+      b.pvx[k] = cur.pvx[i];
+      b.pvy[k] = cur.pvy[i];
+    }
+  }
+}
+
+// header of a send buffer: [0] = number of packed agents, [1] = "this rank has failed" (so that a failure
+// reaches the neighbours with the next exchange and the whole job stops within `world` steps)
+__global__ void halo_header_kernel(HaloBuf left, HaloBuf right, const DevStatus* status) {
+  left.count[0] = 0u;
+  right.count[0] = 0u;
+  left.count[1] = status->failed;
+  right.count[1] = status->failed;
+}
+
+// appends the ghosts of both received buffers after the owned agents; cnt[CNT_TOT] = owned + ghosts
+__global__ void halo_unpack_kernel(AgentArrays cur, uint32_t cap, HaloBuf left, HaloBuf right, int has_left,
+                                   int has_right, uint32_t* cnt, DevStatus* status) {
+  if (status->failed) return;
+  if ((has_left && left.count[1]) || (has_right && right.count[1])) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) status->failed = 1;  // a neighbour failed: stop here too
+    return;
+  }
+  const uint32_t n0 = cnt[CNT_CUR];
+  uint32_t nl = has_left ? left.count[0] : 0u, nr = has_right ? right.count[0] : 0u;
+  if (nl > left.cap) nl = left.cap;
+  if (nr > right.cap) nr = right.cap;
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k == 0) {
+    uint32_t tot = n0 + nl + nr;
+    if (tot > cap) {
+      atomicAdd(&status->capacity_err, 1u);
+      tot = cap;
+    }
+    cnt[CNT_TOT] = tot;
+  }
+  if (k >= nl + nr) return;
+  const HaloBuf& b = k < nl ? left : right;
+  const uint32_t e = k < nl ? k : k - nl;
+  const uint32_t slot = n0 + k;
+  if (slot >= cap) return;
+  cur.x[slot] = b.x[e];
+  cur.y[slot] = b.y[e];
+  cur.vx[slot] = b.vx[e];
+  cur.vy[slot] = b.vy[e];
+  cur.id[slot] = b.id[e];
+  cur.grp[slot] = (uint32_t)(b.meta[e] & 0xffffffffull);
+  cur.wp[slot] = (uint32_t)(b.meta[e] >> 32);
+  if (cur.pvx) {
+    cur.pvx[slot] = b.pvx[e];
+    cur.pvy[slot] = b.pvy[e];
+  }
 }
 
 // FP64 pipe peak: independent DFMA / DADD chains.

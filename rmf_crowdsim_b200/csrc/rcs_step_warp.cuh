@@ -17,9 +17,9 @@
 //            following a per-owner chain in append order = the canonical neighbour order, so the sum is
 //            bit-identical to the sequential one.
 //
-// Agents whose stencil has more than 3 columns (eyesight > cell size) or more than 128 candidates take
-// zanlungo_sequential() inside the same kernel.  Same arithmetic, same order, same results as
-// step_kernel -- tests compare the two bit for bit.
+// Agents whose stencil has more than 3 columns (eyesight > cell size) or more than 128 candidates are put
+// on a device-side list and finished by step_slow_kernel with the sequential routine.  Same arithmetic,
+// same order, same results as step_kernel -- tests compare the two bit for bit.
 #pragma once
 
 #include "rcs_kernels.cuh"
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 4) step_warp_kernel(StepArgs a)
   const unsigned FULL = 0xffffffffu;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t n_live = *a.n_sorted;
-  const bool active = (i < a.n) && (i < n_live);
+  bool active = (i < a.n) && (i < n_live);
 
   const double* __restrict__ xs = a.in.x;
   const double* __restrict__ ys = a.in.y;
@@ -67,15 +67,24 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 4) step_warp_kernel(StepArgs a)
   Self me;
   me.px = me.py = me.vx = me.vy = me.pfx = me.pfy = 0.0;
   me.id = 0;
-  double velx = 0.0, vely = 0.0, thr2 = 0.0, inv_mass = 0.0, rr = 0.0;
-  uint32_t grp = 0;
+  double velx = 0.0, vely = 0.0, thr2 = 0.0, rr = 0.0;
+  uint32_t grp = 0, role = ROLE_PASSIVE;
   bool zan = false;
-  // candidate slices of this lane (cooperative path): [s0,s0+len0) ++ [s1,..) ++ [s2,..)
-  uint32_t s0 = 0, s1 = 0, s2 = 0, len0 = 0, len01 = 0, total = 0;
+  // candidate slices of this lane (cooperative path): flat index t -> j = t + (off0 | off1 | off2)
+  uint32_t off0 = 0, off1 = 0, off2 = 0, len0 = 0, len01 = 0, total = 0;
   bool fast = false;
   uint32_t cand = 0, nbc = 0;
   double t_i = RCS_INF, fx = 0.0, fy = 0.0;
 
+  if (active) {
+    role = agent_role(a, i);
+    if (role == ROLE_PASSIVE) {
+      active = false;
+      if (a.keep) a.keep[i] = 0u;
+    }
+  } else if (a.keep && i < a.n) {
+    a.keep[i] = 0u;
+  }
   if (active) {
     grp = a.in.grp[i];
     const GroupDev& g = a.groups[grp];
@@ -87,7 +96,6 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 4) step_warp_kernel(StepArgs a)
     high_level_velocity(a, i, g, me, velx, vely);
     zan = g.lp_kind == LP_ZANLUNGO;
     thr2 = g.thr2;
-    inv_mass = g.inv_mass;
     rr = g.rr;
     if (zan) {
       int64_t left, right, bottom, top;
@@ -96,35 +104,34 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 4) step_warp_kernel(StepArgs a)
       if (right > a.grid.x_max) right = a.grid.x_max;
       fast = (right - left) <= 2;
       if (fast) {
-        uint32_t ss[3] = {0, 0, 0}, ll[3] = {0, 0, 0};
-        int k = 0;
-        for (int64_t cx = left; cx <= right; ++cx, ++k) {
+        uint32_t s[3] = {0, 0, 0}, l[3] = {0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
           uint64_t c_lo, c_hi;
-          if (column_cell_range(a.grid, cx, bottom, top, c_lo, c_hi)) {
-            ss[k] = cell_start[c_lo];
-            ll[k] = cell_start[c_hi + 1] - ss[k];
+          if (left + k <= right && column_cell_range(a.grid, left + k, bottom, top, c_lo, c_hi)) {
+            s[k] = cell_start[c_lo];
+            l[k] = cell_start[c_hi + 1] - s[k];
           }
         }
-        s0 = ss[0];
-        s1 = ss[1];
-        s2 = ss[2];
-        len0 = ll[0];
-        len01 = ll[0] + ll[1];
-        total = len01 + ll[2];
-        if (total > SW_MAXC) {
-          fast = false;
-          total = 0;
-        } else {
-          cand = total;
-        }
+        len0 = l[0];
+        len01 = l[0] + l[1];
+        total = len01 + l[2];
+        off0 = s[0];
+        off1 = s[1] - len0;
+        off2 = s[2] - len01;
+        fast = total <= SW_MAXC;
       }
       if (!fast) {
-        // wide stencil or crowded cells: sequential reference routine for this agent
-        zanlungo_sequential(a, i, me, g, t_i, fx, fy, nbc, cand);
+        // wide stencil or crowded cells: this agent is finished by step_slow_kernel (sequential routine)
+        total = 0;
+        active = false;
+        zan = false;
+        a.slow_list[atomicAdd(&a.status->slow_count, 1u)] = i;
+      } else {
+        cand = total;
       }
     }
   }
-  __syncwarp();
   w.px[lane] = me.px;
   w.py[lane] = me.py;
   w.vx[lane] = me.vx;
@@ -141,7 +148,7 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 4) step_warp_kernel(StepArgs a)
   const uint32_t maxtot = __reduce_max_sync(FULL, total);
   if (maxtot) {
     // ---------------- phase 1: t_i = min over neighbours of time_to_collision (zanlungo.rs:76-91)
-    unsigned long long mlo = 0ull, mhi = 0ull;  // which of my candidates are neighbours
+    uint32_t nm0 = 0, nm1 = 0, nm2 = 0, nm3 = 0;  // which of my (<= 128) candidates are neighbours
     uint32_t cnt = 0;
     auto flush_ttc = [&]() {
       __syncwarp();
@@ -157,27 +164,34 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 4) step_warp_kernel(StepArgs a)
       __syncwarp();
       cnt = 0;
     };
-    for (uint32_t t = 0; t < maxtot; ++t) {
-      bool pass = false;
-      uint32_t j = 0;
-      if (t < total) {
-        j = t < len0 ? s0 + t : (t < len01 ? s1 + (t - len0) : s2 + (t - len01));
-        const double dx = xs[j] - me.px;
-        const double dy = ys[j] - me.py;
-        const double d2 = dx * dx + dy * dy;
-        pass = (d2 < thr2) && (j != i);  // strict radius filter (:251) and self filter (lib.rs:284)
+    for (uint32_t tb = 0; tb < maxtot; tb += 32) {  // tb is warp-uniform: one mask word per 32 candidates
+      uint32_t word = 0;
+      const uint32_t tend = min(maxtot, tb + 32);
+      for (uint32_t t = tb; t < tend; ++t) {
+        bool pass = false;
+        uint32_t j = 0;
+        if (t < total) {
+          j = t + (t < len0 ? off0 : (t < len01 ? off1 : off2));
+          const double dx = xs[j] - me.px;
+          const double dy = ys[j] - me.py;
+          const double d2 = dx * dx + dy * dy;
+          pass = (d2 < thr2) && (j != i);  // strict radius filter (:251) and self filter (lib.rs:284)
+        }
+        const unsigned m = __ballot_sync(FULL, pass);
+        if (pass) {
+          word |= 1u << (t - tb);
+          const uint32_t pos = cnt + __popc(m & lt_mask);
+          w.lj[pos] = j;
+          w.lo[pos] = (uint8_t)lane;
+        }
+        cnt += __popc(m);
+        if (cnt > SW_PL - 32) flush_ttc();
       }
-      const unsigned m = __ballot_sync(FULL, pass);
-      if (pass) {
-        if (t < 64) mlo |= 1ull << t;
-        else mhi |= 1ull << (t - 64);
-        const uint32_t pos = cnt + __popc(m & lt_mask);
-        w.lj[pos] = j;
-        w.lo[pos] = (uint8_t)lane;
-        nbc++;
-      }
-      cnt += __popc(m);
-      if (cnt > SW_PL - 32) flush_ttc();
+      nbc += __popc(word);
+      if (tb == 0) nm0 = word;
+      else if (tb == 32) nm1 = word;
+      else if (tb == 64) nm2 = word;
+      else nm3 = word;
     }
     if (cnt) flush_ttc();
     __syncwarp();
@@ -198,7 +212,7 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 4) step_warp_kernel(StepArgs a)
         w.f0x[lane] = pre.f0x;
         w.f0y[lane] = pre.f0y;
       } else {
-        mlo = mhi = 0ull;
+        nm0 = nm1 = nm2 = nm3 = 0u;
       }
       __syncwarp();
       uint32_t cntA = 0, cntB = 0;
@@ -258,19 +272,25 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 4) step_warp_kernel(StepArgs a)
         cntB = 0;
       };
       const uint32_t w0_fast = fin ? a.groups[grp].w0_fast : 0u;
-      while (__any_sync(FULL, (mlo | mhi) != 0ull)) {
+      while (__any_sync(FULL, (nm0 | nm1 | nm2 | nm3) != 0u)) {
         bool passA = false, passB = false;
         uint32_t j = 0, lit = 0;
-        if ((mlo | mhi) != 0ull) {
+        if ((nm0 | nm1 | nm2 | nm3) != 0u) {
           uint32_t t;
-          if (mlo) {
-            t = __ffsll((long long)mlo) - 1;
-            mlo &= mlo - 1ull;
+          if (nm0) {
+            t = __ffs(nm0) - 1;
+            nm0 &= nm0 - 1u;
+          } else if (nm1) {
+            t = 32 + __ffs(nm1) - 1;
+            nm1 &= nm1 - 1u;
+          } else if (nm2) {
+            t = 64 + __ffs(nm2) - 1;
+            nm2 &= nm2 - 1u;
           } else {
-            t = 64 + __ffsll((long long)mhi) - 1;
-            mhi &= mhi - 1ull;
+            t = 96 + __ffs(nm3) - 1;
+            nm3 &= nm3 - 1u;
           }
-          j = t < len0 ? s0 + t : (t < len01 ? s1 + (t - len0) : s2 + (t - len01));
+          j = t + (t < len0 ? off0 : (t < len01 ? off1 : off2));
           const uint64_t oid = ids[j];
           double row;
           if (((me.id | oid) >> 53) == 0ull) row = me.id < oid ? -1.0 : 1.0;
@@ -315,14 +335,16 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 4) step_warp_kernel(StepArgs a)
   }
 
   if (active) {
+    const GroupDev& g = a.groups[grp];
     if (zan) {
       // zanlungo.rs:216
-      velx = velx + fx * inv_mass;
-      vely = vely + fy * inv_mass;
+      velx = velx + fx * g.inv_mass;
+      vely = vely + fy * g.inv_mass;
     }
-    integrate_and_store(a, i, me, velx, vely, t_i, fx, fy, nbc);
+    integrate_and_store(a, i, me, g, grp, role, velx, vely, t_i, fx, fy, nbc);
   }
-  warp_stats(a, cand, nbc, (active && zan && t_i != RCS_INF) ? 1u : 0u);
+  const bool own = active && role == ROLE_OWN;
+  warp_stats(a, own ? cand : 0u, own ? nbc : 0u, (own && zan && t_i != RCS_INF) ? 1u : 0u);
 }
 
 }  // namespace rcs

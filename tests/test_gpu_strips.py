@@ -1,0 +1,112 @@
+"""GPU: spatial strips through the single-process transport: every rank count gives
+results BIT-IDENTICAL to a single handle, and the neighbour lists / t_i of owned agents match the oracle."""
+import numpy as np
+import pytest
+
+import parity as P
+import rmf_crowdsim_b200 as R
+from rmf_crowdsim_b200 import scenes as SC
+from rmf_crowdsim_b200.strips import LocalStripGroup, strip_columns
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(st):
+    return {k: (v.view(np.uint64) if v.dtype == np.float64 else v) for k, v in st.items()}
+
+
+def _same(a, b):
+    a, b = _bits(a), _bits(b)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_strips_are_bit_identical_to_one_handle_lane_crowd(world):
+    """40 committed steps of the lane-ordered crowd: agents stream across every strip boundary (1.3 m/s,
+    cells of 2 m), so migration through the redundant ring is exercised in both directions."""
+    scene = SC.uniform_crowd(40, "lane", margin=8.0, seed=9)
+    single = SC.build_simulation(scene)
+    grp = LocalStripGroup(scene, world)
+    dt = R.Duration(0, 100_000_000)  # 0.13 m per step: a boundary crossing every few steps
+    before = [set(sm.read_state()["id"].tolist()) for sm in grp.sims]
+    for _ in range(40):
+        single.step(dt)
+        grp.step(dt)
+    _same(single.read_state(), grp.read_state())
+    assert sum(grp.agent_counts()) == scene.n
+    after = [set(sm.read_state()["id"].tolist()) for sm in grp.sims]
+    assert all(a != b for a, b in zip(after, before))  # agents really migrated, in both directions
+    assert set().union(*after) == set(range(scene.n))
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_strips_shuffled_crowd_forces_match_single_handle_and_oracle(world):
+    scene = SC.uniform_crowd(48, "shuffled", margin=8.0, seed=4)
+    single = SC.build_simulation(scene)
+    grp = LocalStripGroup(scene, world)
+    single.set_trace(True)
+    grp.set_trace(True)
+    dt = R.Duration(*scene.dt)
+    for _ in range(2):
+        single.step(dt)
+        grp.step(dt)
+        tg, ts = grp.read_trace(), single.read_trace()
+        for k in ("id", "nb_offsets", "nb_ids"):
+            assert np.array_equal(tg[k], ts[k]), k
+        for k in ("t_i", "fx", "fy"):
+            assert np.array_equal(tg[k].view(np.uint64), ts[k].view(np.uint64)), k
+        _same(single.read_state(), grp.read_state())
+    # first step against the oracle (identical inputs): neighbour sets and t_i bit-exact, forces 1e-9
+    grp2 = LocalStripGroup(scene, world)
+    grp2.set_trace(True)
+    o2 = P.build_oracle(scene)
+    o2.enable_trace(True)
+    grp2.step(dt)
+    o2.step(*scene.dt)
+    r = P.compare_traces(grp2.read_trace(), o2.read_trace())
+    assert r["finite_tti"] > 0 and r["force_rel_err"] <= P.REL_TOL
+    s = P.compare_states(grp2.read_state(), o2.read_state())
+    assert s["vel_rel_err"] <= P.REL_TOL and s["pos_rel_err"] <= P.REL_TOL
+
+
+def test_no_commit_keeps_the_owned_snapshot():
+    scene = SC.uniform_crowd(32, "shuffled", margin=8.0, seed=2)
+    grp = LocalStripGroup(scene, 3)
+    before = grp.read_state()
+    for _ in range(3):
+        grp.step(R.Duration(*scene.dt), no_commit=True)
+    _same(before, grp.read_state())
+
+
+def test_strip_ranges_tile_the_grid():
+    sim = R.Simulation(R.LocationHash2D(100.0, 100.0, 2.0, (0.0, 0.0), capacity=16))
+    for world in (1, 2, 3, 7, 8):
+        edges = [strip_columns(sim, r, world) for r in range(world)]
+        assert edges[0][0] == 0 and edges[-1][1] == 50
+        assert all(edges[r][1] == edges[r + 1][0] for r in range(world - 1))
+
+
+def test_agent_outside_the_strip_is_rejected():
+    scene = SC.uniform_crowd(16, "lane", margin=8.0)
+    grp = LocalStripGroup(scene, 2)
+    sm = grp.sims[0]
+    with pytest.raises(R.CrowdsimError):
+        # column far right belongs to rank 1
+        from rmf_crowdsim_b200.strips import add_agents_with_ids
+        add_agents_with_ids(sm, np.array([10**6], dtype=np.uint64), np.array([[20.0, 3.0]]), None,
+                            *sm._scene_planners, 2.0)
+
+
+def test_failure_on_one_rank_stops_the_group():
+    """An agent pushed out of the grid on the last rank: that rank reports the reference's error, the other
+    ranks stop within `world` steps through the flag in the halo header."""
+    scene = SC.uniform_crowd(16, "lane", margin=8.0)
+    scene.hl = ("constant", (50.0, 0.0))  # 5 m per step to the right: leaves the 32 m grid quickly
+    grp = LocalStripGroup(scene, 2)
+    codes = set()
+    with pytest.raises(R.CrowdsimError) as e:
+        for _ in range(20):
+            grp.step(R.Duration(0, 100_000_000))
+    codes.add(e.value.code)
+    assert codes & {R._native.RCS_ERR_OUT_OF_BOUNDS, R._native.RCS_ERR_HALO}
