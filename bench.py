@@ -7,8 +7,10 @@ One JSON line on stdout (rank 0).  A "step" is one pass of the whole hot path (L
 radius query, Zanlungo force, Euler integration) over the synthetic crowd.
 
 Workloads (BASELINE.json configs):
-  N = 1 : C3 -- 2^20 agents, uniform density 1/m^2 (jittered lattice), Zanlungo, shuffled ids.
-  N > 1 : C4 -- 2^24 agents total, spatial strips over the N GPUs (strong scaling).
+  default, every N : C4 -- 2^24 agents, 4096 m x 4096 m, density 1/m^2 (jittered lattice), Zanlungo, shuffled
+                     ids, bidirectional +-x flow by id parity.  N > 1: spatial strips over the N GPUs with
+                     an NCCL halo exchange (strong scaling: the crowd is the same for every N).
+  --workload c3    : 2^20 agents (single-GPU roofline study), --workload c2: 10^4 agents.
 The shuffled crowd is timed in frozen-snapshot mode (RCS_STEP_NO_COMMIT): the reference model itself drives
 a dense mixed bidirectional crowd non-finite within 3-23 steps, so every timed step
 runs the full pipeline on the same physical snapshot and discards the result.  `--variant lane` times the
@@ -161,7 +163,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    workload = args.workload or ("c3" if args.gpus == 1 else "c4")
+    workload = args.workload or "c4"
     scene, sample = cpu_sample_scene(workload, args.variant, args.steps + args.warmup)
     value, total = oracle_run(scene, args.steps, max(args.warmup, 1))
     cores = os.cpu_count()
@@ -169,7 +171,7 @@ def run_reference(args):
         "impl": "reference", "metric": "agent-steps/sec (query+Zanlungo+integrate)", "value": value,
         "unit": "agent-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
-        "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(workload, args.variant), "sample": sample},
         "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": 1, "kind": "port", "sample": sample,
                          "host_cores_available": cores,
@@ -198,7 +200,7 @@ def run_gpu_single(args):
     from rmf_crowdsim_b200 import Duration, _native as N
     from rmf_crowdsim_b200 import scenes as SC
 
-    workload = args.workload or "c3"
+    workload = args.workload or "c4"
     scene = make_scene(workload, args.variant, lp_none=args.no_local_plan)
     # committed steps only for the lane-ordered Zanlungo crowd (stays finite); everything else is timed on a
     # frozen snapshot so that agents cannot walk out of the hash domain during a long run
@@ -276,7 +278,7 @@ def run_gpu_single(args):
         except Exception:
             traffic = None
     roofline = {
-        "bound": "hbm", "kernel": "step_kernel (radius query + Zanlungo + Euler, fused)",
+        "bound": "hbm", "kernel": "step_warp_kernel + step_slow_kernel (radius query + Zanlungo + Euler, fused)",
         "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
         "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "peak_source": how, "traffic": traffic,
         "algorithmic_bytes_per_agent_step": algo, "kernel_ms": k_ms, "kernel_share_of_step": k_ms * K / total_ms,
@@ -293,7 +295,7 @@ def run_gpu_single(args):
     line = {
         "metric": "agent-steps/sec (query+Zanlungo+integrate)", "value": value, "unit": "agent-steps/s",
         "n_gpus": 1, "steps": K, "warmup": args.warmup, "ms_per_step": total_ms / K, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {
             "workload": workload_name(workload, args.variant) + (", NoLocalPlan" if args.no_local_plan else ""),
             "agents": n, "mode": "frozen snapshot (RCS_STEP_NO_COMMIT)" if frozen else "committed steps",

@@ -1,0 +1,234 @@
+"""bench.py --gpus N (N > 1): one process per GPU (torchrun), spatial strips with NCCL halo exchange.
+
+torch.distributed is plumbing only: it carries the 128-byte NCCL id from rank 0 to the others and the
+max-over-ranks of the device-timed region.  The halo exchange itself is ncclSend/ncclRecv issued by
+librcs.so on the simulation's own stream (rmf_crowdsim_b200/csrc/rcs_host_dist.inl).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import time
+
+import numpy as np
+
+
+def strip_scene(workload: str, variant: str, rank: int, world: int, lp_none: bool):
+    """The agents of this rank's strip only (the crowd generator is counter-based, scenes.py): returns
+    (scene-without-agents, ids, xy, vxy) for lattice columns that can fall into the strip."""
+    from . import scenes as SC
+
+    side = {"c4": 4096, "c3": 1024, "c2": 100}.get(workload)
+    if side is None and workload.startswith("side"):
+        side = int(workload[4:])
+    margin = 32.0 if workload == "c2" else 64.0
+    s, cell, speed, seed = 1.0, 2.0, 1.3, 1
+    dom = float(np.ceil((side * s + 2 * margin) / cell) * cell)
+    ncols = int(dom / cell)
+    c0, c1 = ncols * rank // world, ncols * (rank + 1) // world
+    # lattice column i sits at x in (i*s, (i+1)*s): cell column floor((x + margin) / cell)
+    i0 = max(0, int(np.floor(c0 * cell - margin)) - 1)
+    i1 = min(side, int(np.ceil(c1 * cell - margin)) + 1)
+    xy = SC.jittered_lattice(side, side, s, seed, i0, i1)
+    ids = SC.site_ids(side, side, variant, seed, i0, i1)
+    par = (ids % np.uint64(2)).astype(np.float64)
+    vxy = np.zeros_like(xy)
+    vxy[:, 0] = np.where(par == 0, -speed, speed)
+    scene = SC.Scene(name=f"{workload}_{variant}_strip{rank}", width=dom, height=dom, cell=cell,
+                     offset=(-margin, -margin), xy=np.zeros((0, 2)), vxy=np.zeros((0, 2)), eyesight=2.0,
+                     hl=("parity", (speed, 0.0)),
+                     lp=("none",) if lp_none else ("zanlungo", 0.05, 1.0, 0.0, 0.5, 1.0, 0.2), seed=seed)
+    return scene, side * side, ids, xy, vxy
+
+
+def run(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from . import _native as N
+    from . import sim as S
+    from .strips import StripSimulation, owned_mask
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nccl_id = fresh_nccl_id(dist, torch, rank)
+
+    workload = args.workload or "c4"
+    frozen = not (args.variant == "lane" and not args.no_local_plan)
+    scene, n_total, ids, xy, vxy = strip_scene(workload, args.variant, rank, world, args.no_local_plan)
+    ncols = int(scene.width / scene.cell)
+    c0, c1 = ncols * rank // world, ncols * (rank + 1) // world
+    m = owned_mask(xy[:, 0], scene.offset[0], scene.cell, c0, c1)
+    n_own = int(m.sum())
+    # room for the owned agents, three ghost columns per side and the churn of a long committed run
+    per_col = int(round(n_total ** 0.5)) * scene.cell  # agents per cell column at spacing 1 m
+    halo_cap = int(4 * per_col * 1.5) + 4096
+    cap = int(n_own * 1.05) + 2 * halo_cap + 4096
+    idx = S.LocationHash2D(scene.width, scene.height, scene.cell, scene.offset, capacity=cap, device=local)
+    sim = StripSimulation(idx, rank, world, nccl_id, halo_capacity=halo_cap)
+    assert (sim.c0, sim.c1) == (c0, c1)
+    sim.add_scene_agents(scene, ids, xy, vxy)
+    lib, h = sim._lib, sim._h
+    dt = S.Duration(*scene.dt)
+    flags = N.RCS_STEP_NO_COMMIT if frozen else N.RCS_STEP_DEFAULT
+
+    def one_step():
+        N.check(h, lib.rcs_step_async(h, dt.secs, dt.nanos, flags))
+
+    from bench import ClockSampler  # the launcher module (repo root is on sys.path)
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    sim.sync()
+    clocks = ClockSampler(local)
+    clocks.start()
+    for _ in range(4):  # a little load before the timed region so that the clock samples are meaningful
+        for _ in range(8):
+            one_step()
+        sim.sync()
+    launches0 = sim.launch_count()
+    N.check(h, lib.rcs_kernel_timing(h, 1))
+    K = args.steps
+    dist.barrier()
+    torch.cuda.synchronize()
+    sim.sync()
+    wall0 = time.perf_counter()
+    sim.event_record(0)
+    for _ in range(K):
+        one_step()
+    sim.event_record(1)
+    sim.sync()
+    torch.cuda.synchronize()
+    dist.barrier()
+    wall1 = time.perf_counter()
+    ms = torch.tensor([sim.event_elapsed_ms(0, 1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    kt_ms, kt_n = C.c_double(), C.c_uint64()
+    N.check(h, lib.rcs_kernel_time_ms(h, C.byref(kt_ms), C.byref(kt_n)))
+    N.check(h, lib.rcs_kernel_timing(h, 0))
+    launches = sim.launch_count() - launches0
+    st = sim.stats()
+    clk = clocks.stop()
+
+    # per-rank statistics -> global
+    agg = torch.tensor([st.neighbour_total, st.candidate_total, st.finite_tti_count, st.nonfinite_count,
+                        st.oob_count, sim.agent_count(), launches], dtype=torch.float64, device="cuda")
+    dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    kmax = torch.tensor([kt_ms.value / max(kt_n.value, 1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(kmax, op=dist.ReduceOp.MAX)
+
+    e2e = None
+    if not args.skip_e2e:
+        sim.spatial_index.close()
+        scene.hl = ("host", scene.hl[1])
+        idx2 = S.LocationHash2D(scene.width, scene.height, scene.cell, scene.offset, capacity=cap, device=local)
+        sim2 = StripSimulation(idx2, rank, world, fresh_nccl_id(dist, torch, rank), halo_capacity=halo_cap)
+        sim2.add_scene_agents(scene, ids, xy, vxy)
+        e2e = run_e2e(sim2, scene, min(K, 10), 3, dist, torch)
+
+    if rank == 0:
+        from bench import ALGO_BYTES_NOLOCALPLAN, ALGO_BYTES_ZANLUNGO, measured_peaks, workload_name
+
+        peaks, how = measured_peaks()
+        algo = ALGO_BYTES_NOLOCALPLAN if args.no_local_plan else ALGO_BYTES_ZANLUNGO
+        n_live = int(agg[5].item())
+        value = n_live * K / (total_ms * 1e-3)
+        k_ms = float(kmax.item())
+        achieved = algo * (n_live / world) / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
+        line = {
+            "metric": "agent-steps/sec (query+Zanlungo+integrate)", "value": value, "unit": "agent-steps/s",
+            "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": total_ms / K,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": workload_name(workload, args.variant) + (", NoLocalPlan" if args.no_local_plan else ""),
+                "agents": n_live, "agents_per_gpu": n_live / world,
+                "parallelism": f"{world} spatial strips along x, NCCL send/recv halo (3 cell columns per side), "
+                               "ring agents advanced redundantly (no migration message)",
+                "mode": "frozen snapshot (RCS_STEP_NO_COMMIT)" if frozen else "committed steps",
+                "l2": "per-rank working set (two state buffer sets + index) larger than L2; no flush between steps",
+                "seed": scene.seed, "dt_ns": scene.dt[1],
+                "mean_neighbours": agg[0].item() / max(n_live, 1), "candidates_per_agent": agg[1].item() / max(n_live, 1),
+                "finite_tti_fraction": agg[2].item() / max(n_live, 1), "nonfinite": int(agg[3].item()),
+                "oob": int(agg[4].item()),
+            },
+            "e2e": e2e, "gpu_launches": int(agg[6].item()),
+            "roofline": {
+                "bound": "hbm", "kernel": "step_warp_kernel (+ step_slow_kernel) per rank, slowest rank",
+                "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "peak_source": how, "traffic": None,
+                "algorithmic_bytes_per_agent_step": algo, "kernel_ms": k_ms,
+                "kernel_share_of_step": k_ms * K / total_ms,
+                "note": "the Zanlungo kernel is FP64-pipe / latency bound, not HBM-bound (DESIGN.md)",
+            },
+            "cpu_baseline": None, "clocks": clk, "wall_s_timed_region": wall1 - wall0,
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def fresh_nccl_id(dist, torch, rank: int) -> bytes:
+    from .strips import nccl_unique_id
+
+    ident = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        ident = torch.tensor(list(nccl_unique_id()), dtype=torch.uint8, device="cuda")
+    dist.broadcast(ident, 0)
+    return bytes(ident.cpu().tolist())
+
+
+def run_e2e(sim, scene, steps: int, warmup: int, dist, torch) -> dict:
+    """End to end per rank with HOST buffers, every step: upload the preferred velocities of a host-side
+    HighLevelPlanner for the rank's agents (pinned -> device), run the step, read x,y,vx,vy of the rank's
+    agents back (device -> pinned).  Frozen snapshot, so every rank keeps its agent set."""
+    from . import _native as N
+    from .sim import Duration
+
+    lib, h = sim._lib, sim._h
+    n = sim.agent_count()
+    ids = sim.read_state()["id"]
+
+    def pinned(count):
+        p = C.c_void_p()
+        N.check(None, lib.rcs_host_alloc(max(count, 1) * 8, C.byref(p)))
+        arr = np.frombuffer((C.c_char * (max(count, 1) * 8)).from_address(p.value), dtype=np.float64, count=count)
+        return arr, p
+
+    pref, pref_p = pinned(2 * n)
+    outs = [pinned(n) for _ in range(4)]
+    speed = scene.hl[1]
+    par = (ids % np.uint64(2)) == 0
+    pref[0::2] = np.where(par, -speed[0], speed[0])
+    pref[1::2] = np.where(par, -speed[1], speed[1])
+    d = Duration(*scene.dt)
+    out_n = C.c_uint64()
+
+    def one():
+        N.check(h, lib.rcs_set_preferred_velocity(h, n, None, pref.ctypes.data_as(N.c_f64p)))
+        N.check(h, lib.rcs_step_async(h, d.secs, d.nanos, N.RCS_STEP_NO_COMMIT))
+        N.check(h, lib.rcs_read_agents(h, N.RCS_ORDER_ID, n, None, *[o[0].ctypes.data_as(N.c_f64p) for o in outs],
+                                       None, C.byref(out_n)))
+
+    for _ in range(warmup):
+        one()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dist.barrier()
+    t1 = time.perf_counter()
+    t = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tot = torch.tensor([float(n)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    for _, p in [(pref, pref_p)] + outs:
+        lib.rcs_host_free(p)
+    return {"value": tot.item() * steps / t.item(), "unit": "agent-steps/s",
+            "h2d_bytes_per_step": int(16 * tot.item()), "d2h_bytes_per_step": int(32 * tot.item()), "steps": steps,
+            "path": "per rank: rcs_set_preferred_velocity(pinned host) + rcs_step_async + "
+                    "rcs_read_agents(ORDER_ID, pinned host); max over ranks of the wall time"}

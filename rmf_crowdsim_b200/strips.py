@@ -50,9 +50,14 @@ def add_agents_with_ids(sim: S.Simulation, ids: np.ndarray, xy: np.ndarray, vxy:
                                                  float(eyesight)))
 
 
+class HostPlan(S.HighLevelPlanner):
+    """A HighLevelPlanner evaluated by the caller: its results are uploaded with set_preferred_velocity."""
+
+
 def _planners(scene):
     kind, v = scene.hl
-    hl = {"parity": S.ParityVelocityPlan, "constant": S.ConstantVelocityPlan}[kind](v)
+    hl = HostPlan() if kind == "host" else {"parity": S.ParityVelocityPlan,
+                                            "constant": S.ConstantVelocityPlan}[kind](v)
     lp = S.NoLocalPlan() if scene.lp[0] == "none" else S.Zanlungo(*scene.lp[1:])
     return hl, lp
 
