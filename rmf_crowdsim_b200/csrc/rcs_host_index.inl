@@ -93,12 +93,12 @@ int rcs_query_knn(rcs_sim* s, uint64_t nq, const double* qxy, uint64_t k, uint64
   int rc = ensure_index(s);
   if (rc) return rc;
   // stage: qxy (16 nq) | counts (4 (nq+1)) | offsets (4 (nq+1))
-  rc = ensure_stage(s, nq * 24 + 64);
+  rc = ensure_stage(s, nq * 24 + 128);
   if (rc) return rc;
   char* base = static_cast<char*>(s->stage);
   double* d_q = reinterpret_cast<double*>(base);
   uint32_t* d_c = reinterpret_cast<uint32_t*>(base + nq * 16);
-  uint32_t* d_o = d_c + nq + 1;
+  uint32_t* d_o = d_c + ((nq + 1 + 3) & ~3ull);  // the scan kernels use 16-byte vector accesses
   CU_TRY(s, cudaMemcpyAsync(d_q, qxy, nq * 16, cudaMemcpyHostToDevice, s->stream));
   knn_count_kernel<<<blocks_for(nq, 128), 128, 0, s->stream>>>(s->grid, s->cell_start, (uint32_t)nq, d_q, k, d_c);
   s->launches += 1;

@@ -2,51 +2,55 @@
 //
 // step_kernel (rcs_kernels.cuh) gives each agent one thread that walks its own candidates and runs
 // time_to_collision / the pair force inline; ncu shows those bodies executing with 3-5 of 32 lanes
-// (profiles/r01a_step_kernel_v1.md).  Here a warp owns 32 consecutive agents of the canonical
-// (cell, id) order and splits the work in two kinds of stages:
+// (profiles/r01a_step_kernel_v1.md).  Here a warp owns 32 consecutive agents of the canonical (cell, id) order.
+// The work is split by cost so that cheap, frequent tests stay per lane with no bookkeeping and only the rare,
+// expensive bodies are compacted across the warp (profiles/r01b_step_warp_kernel_v3.md explains why):
 //
-//   filter : every lane walks its own agent's candidates -- at most three contiguous slices of the
-//            sorted arrays, one per stencil column -- with a flat counter (2 loads, 5 DP ops, 1 compare
-//            per candidate).  Pairs that pass the strict radius test + self filter are (a) recorded in a
-//            per-lane 128-bit mask for the force pass and (b) compacted with warp ballots into a
-//            shared-memory (owner lane, neighbour index) list;
-//   dense  : the list is processed one pair per lane, so time_to_collision (phase 1) and the pair force
-//            (phase 2) run with all lanes busy.  t_i is reduced with a shared 64-bit atomicMin on the bit
-//            pattern (all collision times are >= +0, so integer order == floating order and min is
-//            order-independent); pair forces go to per-pair slots and every owner adds its own slots by
-//            following a per-owner chain in append order = the canonical neighbour order, so the sum is
-//            bit-identical to the sequential one.
+//   1 filter   every lane walks its own candidates -- three contiguous slices of the sorted arrays, one per
+//              stencil column -- and records the strict radius test (location_hash_2d.rs:251) + self filter
+//              (lib.rs:284) as one 32-bit mask per slice.  2 loads, 5 DP ops, 2 compares per candidate.
+//   2 t_i      every lane walks its own neighbour bits and evaluates the division-free half of
+//              time_to_collision (zanlungo.rs:49-60: a, b, c, discriminant).  Only pairs that can return a
+//              finite time (a > 0, discriminant >= 0, larger root possibly positive: ~15 % of the neighbours)
+//              are compacted with a ballot into a shared pair list; the list is processed one pair per lane with
+//              the literal routine (sqrt, two divisions, root selection) and reduced per owner with a 64-bit
+//              shared atomicMin on the bit pattern (collision times are >= +0, so integer order == float order,
+//              and min is order-independent).  The same walk records which neighbours have the higher id.
+//   3 force    owners with a finite t_i split their neighbour bits into yield pairs (own id lower: weight 2,
+//              real force, zanlungo.rs:93-170) and weight-0 pairs (provably (+-0, +-0) in the common case,
+//              rcs_math.cuh).  Both kinds are compacted into their own lists and evaluated one pair per lane.
+//              Pair forces go to per-pair slots; every owner adds its own slots by following a chain in append
+//              order = canonical neighbour order, so the sum is bit-identical to the sequential one.
 //
-// Agents whose stencil has more than 3 columns (eyesight > cell size) or more than 128 candidates are put
-// on a device-side list and finished by step_slow_kernel with the sequential routine.  Same arithmetic,
-// same order, same results as step_kernel -- tests compare the two bit for bit.
+// Agents whose stencil has more than 3 columns (eyesight > cell size) or a slice with more than 32 candidates are
+// put on a device-side list and finished by step_slow_kernel with the sequential routine.  Same arithmetic, same
+// order, same results as step_kernel -- tests compare the two bit for bit.
 #pragma once
 
 #include "rcs_kernels.cuh"
 
 namespace rcs {
 
-constexpr int SW_WARPS = 4;       // warps per block
-constexpr int SW_PL = 512;        // phase-1 pair list entries per warp
-constexpr int SW_PLA = 128;       // phase-2 list A (pairs that need a real force evaluation)
-constexpr int SW_PLB = 128;       // phase-2 list B (weight-0 pairs: only the "is it exactly zero" check)
-constexpr uint32_t SW_MAXC = 128; // candidates per agent on the cooperative path (mask width)
+constexpr int SW_WARPS = 4;            // warps per block
+constexpr int SW_LIST = 96;            // entries per pair list; flushed when more than SW_LIST - 32 are queued
+constexpr uint32_t SW_SLICE_MAX = 32;  // candidates per stencil column on the cooperative path (mask width)
 constexpr uint32_t SW_NONE = 0xffffu;
 
 struct WarpShared {
-  double px[32], py[32], vx[32], vy[32], pfx[32], pfy[32], ti[32], rr[32];
-  double futx[32], futy[32], mag[32], mvx[32], mvy[32], f0x[32], f0y[32];  // OwnerPre
+  double px[32], py[32], vx[32], vy[32], rr[32];                              // owners (stages 2 and 3)
+  double pfx[32], pfy[32], ti[32];
+  double futx[32], futy[32], mag[32], mvx[32], mvy[32], f0x[32], f0y[32];     // OwnerPre (stage 3)
   unsigned long long id[32];
   unsigned long long tbits[32];
-  double sfx[SW_PLA], sfy[SW_PLA];
-  uint32_t lj[SW_PL];
+  double sfx[SW_LIST], sfy[SW_LIST];   // pair forces of list A
+  uint32_t lj[2 * SW_LIST];            // neighbour slot: list A (and the stage-2 hit list) | list B
   uint32_t grp[32];
   unsigned int poison[32];
-  uint16_t nxt[SW_PLA];
-  uint8_t lo[SW_PL];
+  uint16_t nxt[SW_LIST];               // per-owner chain through list A
+  uint8_t lo[2 * SW_LIST];             // owner lane: list A | list B
 };
 
-__global__ void __launch_bounds__(32 * SW_WARPS, 4) step_warp_kernel(StepArgs a) {
+__global__ void __launch_bounds__(32 * SW_WARPS, 5) step_warp_kernel(StepArgs a) {
   if (a.status->failed) return;
   __shared__ WarpShared sh[SW_WARPS];
   WarpShared& w = sh[threadIdx.x >> 5];
@@ -70,8 +74,7 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 4) step_warp_kernel(StepArgs a)
   double velx = 0.0, vely = 0.0, thr2 = 0.0, rr = 0.0;
   uint32_t grp = 0, role = ROLE_PASSIVE;
   bool zan = false;
-  // candidate slices of this lane (cooperative path): flat index t -> j = t + (off0 | off1 | off2)
-  uint32_t off0 = 0, off1 = 0, off2 = 0, len0 = 0, len01 = 0, total = 0;
+  uint32_t s0 = 0, s1 = 0, s2 = 0, l0 = 0, l1 = 0, l2 = 0;  // candidate slices of this lane (cooperative path)
   bool fast = false;
   uint32_t cand = 0, nbc = 0;
   double t_i = RCS_INF, fx = 0.0, fy = 0.0;
@@ -102,7 +105,9 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 4) step_warp_kernel(StepArgs a)
       get_bounds(a.grid, g.eyesight, me.px, me.py, left, right, bottom, top);
       if (left < 0) left = 0;
       if (right > a.grid.x_max) right = a.grid.x_max;
-      fast = (right - left) <= 2;
+      // ids >= 2^53 round when they become priorities (zanlungo.rs:94) and groups whose weight-0 pairs cannot be
+      // proven zero need the literal routine for every pair: both are left to the sequential kernel
+      fast = (right - left) <= 2 && g.w0_fast && (me.id >> 53) == 0ull;
       if (fast) {
         uint32_t s[3] = {0, 0, 0}, l[3] = {0, 0, 0};
 #pragma unroll
@@ -113,93 +118,133 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 4) step_warp_kernel(StepArgs a)
             l[k] = cell_start[c_hi + 1] - s[k];
           }
         }
-        len0 = l[0];
-        len01 = l[0] + l[1];
-        total = len01 + l[2];
-        off0 = s[0];
-        off1 = s[1] - len0;
-        off2 = s[2] - len01;
-        fast = total <= SW_MAXC;
+        s0 = s[0]; s1 = s[1]; s2 = s[2];
+        l0 = l[0]; l1 = l[1]; l2 = l[2];
+        fast = l0 <= SW_SLICE_MAX && l1 <= SW_SLICE_MAX && l2 <= SW_SLICE_MAX;
       }
       if (!fast) {
         // wide stencil or crowded cells: this agent is finished by step_slow_kernel (sequential routine)
-        total = 0;
+        l0 = l1 = l2 = 0;
         active = false;
         zan = false;
         a.slow_list[atomicAdd(&a.status->slow_count, 1u)] = i;
       } else {
-        cand = total;
+        cand = l0 + l1 + l2;
       }
     }
   }
-  w.px[lane] = me.px;
-  w.py[lane] = me.py;
-  w.vx[lane] = me.vx;
-  w.vy[lane] = me.vy;
-  w.pfx[lane] = me.pfx;
-  w.pfy[lane] = me.pfy;
-  w.rr[lane] = rr;
-  w.id[lane] = me.id;
-  w.grp[lane] = grp;
-  w.tbits[lane] = 0x7ff0000000000000ull;
-  w.poison[lane] = 0u;
-  __syncwarp();
 
-  const uint32_t maxtot = __reduce_max_sync(FULL, total);
-  if (maxtot) {
-    // ---------------- phase 1: t_i = min over neighbours of time_to_collision (zanlungo.rs:76-91)
-    uint32_t nm0 = 0, nm1 = 0, nm2 = 0, nm3 = 0;  // which of my (<= 128) candidates are neighbours
-    uint32_t cnt = 0;
-    auto flush_ttc = [&]() {
-      __syncwarp();
-      for (uint32_t e = lane; e < cnt; e += 32) {
-        const uint32_t o = w.lo[e];
-        const uint32_t j = w.lj[e];
-        const double dx = xs[j] - w.px[o];
-        const double dy = ys[j] - w.py[o];
-        const double d2 = dx * dx + dy * dy;
-        const double ct = time_to_collision(vxs[j] - w.vx[o], vys[j] - w.vy[o], dx, dy, d2, w.rr[o]);
-        if (ct < RCS_INF) atomicMin(&w.tbits[o], (unsigned long long)__double_as_longlong(ct));
-      }
-      __syncwarp();
-      cnt = 0;
-    };
-    for (uint32_t tb = 0; tb < maxtot; tb += 32) {  // tb is warp-uniform: one mask word per 32 candidates
-      uint32_t word = 0;
-      const uint32_t tend = min(maxtot, tb + 32);
-      for (uint32_t t = tb; t < tend; ++t) {
-        bool pass = false;
+  // ---------------- stage 1: radius filter, one mask per stencil column
+  uint32_t m0 = 0, m1 = 0, m2 = 0;
+  {
+    const uint32_t x0 = __reduce_max_sync(FULL, l0), x1 = __reduce_max_sync(FULL, l1),
+                   x2 = __reduce_max_sync(FULL, l2);
+#define RCS_FILTER_SLICE(MX, S, L, M)                                  \
+    for (uint32_t t = 0; t < (MX); ++t) {                              \
+      if (t < (L)) {                                                   \
+        const uint32_t j = (S) + t;                                    \
+        const double dx = xs[j] - me.px;                               \
+        const double dy = ys[j] - me.py;                               \
+        const double d2 = dx * dx + dy * dy;                           \
+        if ((d2 < thr2) && (j != i)) (M) |= 1u << t;                   \
+      }                                                                \
+    }
+    RCS_FILTER_SLICE(x0, s0, l0, m0)
+    RCS_FILTER_SLICE(x1, s1, l1, m1)
+    RCS_FILTER_SLICE(x2, s2, l2, m2)
+#undef RCS_FILTER_SLICE
+  }
+  nbc = __popc(m0) + __popc(m1) + __popc(m2);
+
+  if (__any_sync(FULL, (m0 | m1 | m2) != 0u)) {
+    w.px[lane] = me.px;
+    w.py[lane] = me.py;
+    w.vx[lane] = me.vx;
+    w.vy[lane] = me.vy;
+    w.rr[lane] = rr;
+    w.tbits[lane] = 0x7ff0000000000000ull;
+    __syncwarp();
+
+    // ---------------- stage 2: t_i = min over neighbours of time_to_collision (zanlungo.rs:76-91)
+    // neighbours with the higher id: this agent yields to them (right_of_way = -1; exact for own ids < 2^53)
+    uint32_t y0 = 0, y1 = 0, y2 = 0;
+    {
+      uint32_t cnt = 0;
+      auto flush_hits = [&]() {
+        __syncwarp();
+        for (uint32_t e = lane; e < cnt; e += 32) {
+          const uint32_t o = w.lo[e];
+          const uint32_t j = w.lj[e];
+          const double dx = xs[j] - w.px[o];
+          const double dy = ys[j] - w.py[o];
+          const double d2 = dx * dx + dy * dy;
+          const double ct = time_to_collision(vxs[j] - w.vx[o], vys[j] - w.vy[o], dx, dy, d2, w.rr[o]);
+          if (ct < RCS_INF) atomicMin(&w.tbits[o], (unsigned long long)__double_as_longlong(ct));
+        }
+        __syncwarp();
+        cnt = 0;
+      };
+      uint32_t b0 = m0, b1 = m1, b2 = m2;
+      while (__any_sync(FULL, (b0 | b1 | b2) != 0u)) {
+        bool hit = false;
         uint32_t j = 0;
-        if (t < total) {
-          j = t + (t < len0 ? off0 : (t < len01 ? off1 : off2));
+        if ((b0 | b1 | b2) != 0u) {
+          uint32_t t, k;
+          if (b0) {
+            t = __ffs(b0) - 1; b0 &= b0 - 1u; j = s0 + t; k = 0;
+          } else if (b1) {
+            t = __ffs(b1) - 1; b1 &= b1 - 1u; j = s1 + t; k = 1;
+          } else {
+            t = __ffs(b2) - 1; b2 &= b2 - 1u; j = s2 + t; k = 2;
+          }
+          if (me.id < ids[j]) {
+            const uint32_t bit = 1u << t;
+            if (k == 0) y0 |= bit;
+            else if (k == 1) y1 |= bit;
+            else y2 |= bit;
+          }
+          // the division-free half of time_to_collision; same operations as rcs_math.cuh
           const double dx = xs[j] - me.px;
           const double dy = ys[j] - me.py;
-          const double d2 = dx * dx + dy * dy;
-          pass = (d2 < thr2) && (j != i);  // strict radius filter (:251) and self filter (lib.rs:284)
+          const double rvx = vxs[j] - me.vx;
+          const double rvy = vys[j] - me.vy;
+          const double qa = rvx * rvx + rvy * rvy;
+          if (qa > 0.0) {
+            const double d2 = dx * dx + dy * dy;
+            const double qb = 2.0 * (rvx * dx + rvy * dy);
+            const double qc = d2 - rr;
+            const double bb = qb * qb;
+            const double disc = bb - (4.0 * qa) * qc;
+            // A finite time needs disc >= 0 and -b + sqrt(disc) > 0.  For b >= 0, disc <= b*b gives
+            // sqrt(disc) <= sqrt(fl(b*b)) = b (correctly rounded sqrt of a square is exact and monotone), so the
+            // numerator is <= 0: INF (b*b overflowing is excluded from the argument).  Everything else is decided
+            // by the literal routine on the compacted list.
+            hit = (disc >= 0.0) && ((qb < 0.0) || (disc > bb) || !(bb < RCS_INF));
+          }
         }
-        const unsigned m = __ballot_sync(FULL, pass);
-        if (pass) {
-          word |= 1u << (t - tb);
-          const uint32_t pos = cnt + __popc(m & lt_mask);
+        const unsigned hm = __ballot_sync(FULL, hit);
+        if (hit) {
+          const uint32_t pos = cnt + __popc(hm & lt_mask);
           w.lj[pos] = j;
           w.lo[pos] = (uint8_t)lane;
         }
-        cnt += __popc(m);
-        if (cnt > SW_PL - 32) flush_ttc();
+        cnt += __popc(hm);
+        if (cnt > SW_LIST - 32) flush_hits();
       }
-      nbc += __popc(word);
-      if (tb == 0) nm0 = word;
-      else if (tb == 32) nm1 = word;
-      else if (tb == 64) nm2 = word;
-      else nm3 = word;
+      if (cnt) flush_hits();
+      __syncwarp();
+      if (fast) t_i = __longlong_as_double((long long)w.tbits[lane]);
     }
-    if (cnt) flush_ttc();
-    __syncwarp();
-    if (fast) t_i = __longlong_as_double((long long)w.tbits[lane]);
 
-    // ---------------- phase 2: force = sum over neighbours of compute_agent_force (zanlungo.rs:210-215)
+    // ---------------- stage 3: force = sum over neighbours of compute_agent_force (zanlungo.rs:210-215)
     const bool fin = fast && (t_i != RCS_INF);
     if (__any_sync(FULL, fin)) {
+      uint32_t a0 = 0, a1 = 0, a2 = 0, z0 = 0, z1 = 0, z2 = 0;  // list A bits (evaluate) / list B bits (prove zero)
+      w.pfx[lane] = me.pfx;
+      w.pfy[lane] = me.pfy;
+      w.id[lane] = me.id;
+      w.grp[lane] = grp;
+      w.poison[lane] = 0u;
       if (fin) {
         const GroupDev& g = a.groups[grp];
         const OwnerPre pre = owner_precompute(me.px, me.py, me.vx, me.vy, me.pfx, me.pfy, t_i, g);
@@ -211,8 +256,8 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 4) step_warp_kernel(StepArgs a)
         w.mvy[lane] = pre.mvy;
         w.f0x[lane] = pre.f0x;
         w.f0y[lane] = pre.f0y;
-      } else {
-        nm0 = nm1 = nm2 = nm3 = 0u;
+        a0 = m0 & y0; a1 = m1 & y1; a2 = m2 & y2;
+        z0 = m0 & ~y0; z1 = m1 & ~y1; z2 = m2 & ~y2;
       }
       __syncwarp();
       uint32_t cntA = 0, cntB = 0;
@@ -233,15 +278,11 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 4) step_warp_kernel(StepArgs a)
       auto flush_A = [&]() {
         __syncwarp();
         for (uint32_t e = lane; e < cntA; e += 32) {
-          const uint32_t o = w.lo[e] & 31u;
+          const uint32_t o = w.lo[e];
           const uint32_t j = w.lj[e];
           double qx, qy;
-          if ((w.lo[e] >> 5) == 0u) {
-            pair_force_yield(load_pre(o), w.px[o], w.py[o], w.vx[o], w.vy[o], xs[j], ys[j], vxs[j], vys[j], w.ti[o],
-                             a.groups[w.grp[o]], qx, qy);
-          } else {
-            literal(o, j, qx, qy);
-          }
+          pair_force_yield(load_pre(o), w.px[o], w.py[o], w.vx[o], w.vy[o], xs[j], ys[j], vxs[j], vys[j], w.ti[o],
+                           a.groups[w.grp[o]], qx, qy);
           w.sfx[e] = qx;
           w.sfy[e] = qy;
         }
@@ -258,8 +299,8 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 4) step_warp_kernel(StepArgs a)
       auto flush_B = [&]() {
         __syncwarp();
         for (uint32_t e = lane; e < cntB; e += 32) {
-          const uint32_t o = w.lo[SW_PLA + e];
-          const uint32_t j = w.lj[SW_PLA + e];
+          const uint32_t o = w.lo[SW_LIST + e];
+          const uint32_t j = w.lj[SW_LIST + e];
           if (!pair_force_w0_is_zero(load_pre(o), xs[j], ys[j], vxs[j], vys[j], w.ti[o])) {
             // contributes NaN or +-0 per component (rcs_math.cuh): NaN is order-independent
             double qx, qy;
@@ -271,59 +312,44 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 4) step_warp_kernel(StepArgs a)
         __syncwarp();
         cntB = 0;
       };
-      const uint32_t w0_fast = fin ? a.groups[grp].w0_fast : 0u;
-      while (__any_sync(FULL, (nm0 | nm1 | nm2 | nm3) != 0u)) {
+      while (__any_sync(FULL, (a0 | a1 | a2 | z0 | z1 | z2) != 0u)) {
+        // one list-A and one list-B pair per lane and iteration
         bool passA = false, passB = false;
-        uint32_t j = 0, lit = 0;
-        if ((nm0 | nm1 | nm2 | nm3) != 0u) {
-          uint32_t t;
-          if (nm0) {
-            t = __ffs(nm0) - 1;
-            nm0 &= nm0 - 1u;
-          } else if (nm1) {
-            t = 32 + __ffs(nm1) - 1;
-            nm1 &= nm1 - 1u;
-          } else if (nm2) {
-            t = 64 + __ffs(nm2) - 1;
-            nm2 &= nm2 - 1u;
-          } else {
-            t = 96 + __ffs(nm3) - 1;
-            nm3 &= nm3 - 1u;
-          }
-          j = t + (t < len0 ? off0 : (t < len01 ? off1 : off2));
-          const uint64_t oid = ids[j];
-          double row;
-          if (((me.id | oid) >> 53) == 0ull) row = me.id < oid ? -1.0 : 1.0;
-          else row = right_of_way(me.id, oid);
-          if (row < 0.0) {
-            passA = true;
-          } else if (row > 0.0 && w0_fast) {
-            passB = true;
-          } else {
-            passA = true;
-            lit = 1;
-          }
+        uint32_t jA = 0, jB = 0;
+        if (a0) {
+          jA = s0 + __ffs(a0) - 1; a0 &= a0 - 1u; passA = true;
+        } else if (a1) {
+          jA = s1 + __ffs(a1) - 1; a1 &= a1 - 1u; passA = true;
+        } else if (a2) {
+          jA = s2 + __ffs(a2) - 1; a2 &= a2 - 1u; passA = true;
+        }
+        if (z0) {
+          jB = s0 + __ffs(z0) - 1; z0 &= z0 - 1u; passB = true;
+        } else if (z1) {
+          jB = s1 + __ffs(z1) - 1; z1 &= z1 - 1u; passB = true;
+        } else if (z2) {
+          jB = s2 + __ffs(z2) - 1; z2 &= z2 - 1u; passB = true;
         }
         const unsigned mA = __ballot_sync(FULL, passA);
         const unsigned mB = __ballot_sync(FULL, passB);
         if (passA) {
           const uint32_t pos = cntA + __popc(mA & lt_mask);
-          w.lj[pos] = j;
-          w.lo[pos] = (uint8_t)(lane | (lit << 5));
+          w.lj[pos] = jA;
+          w.lo[pos] = (uint8_t)lane;
           w.nxt[pos] = (uint16_t)SW_NONE;
           if (last != SW_NONE) w.nxt[last] = (uint16_t)pos;
           else first = pos;
           last = pos;
         }
         if (passB) {
-          const uint32_t pos = SW_PLA + cntB + __popc(mB & lt_mask);
-          w.lj[pos] = j;
+          const uint32_t pos = SW_LIST + cntB + __popc(mB & lt_mask);
+          w.lj[pos] = jB;
           w.lo[pos] = (uint8_t)lane;
         }
         cntA += __popc(mA);
         cntB += __popc(mB);
-        if (cntA > SW_PLA - 32) flush_A();
-        if (cntB > SW_PLB - 32) flush_B();
+        if (cntA > SW_LIST - 32) flush_A();
+        if (cntB > SW_LIST - 32) flush_B();
       }
       if (cntA) flush_A();
       if (cntB) flush_B();
