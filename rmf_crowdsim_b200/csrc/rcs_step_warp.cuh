@@ -19,8 +19,9 @@
 //   3 force    owners with a finite t_i split their neighbour bits into yield pairs (own id lower: weight 2,
 //              real force, zanlungo.rs:93-170) and weight-0 pairs (provably (+-0, +-0) in the common case,
 //              rcs_math.cuh).  Both kinds are compacted into their own lists and evaluated one pair per lane.
-//              Pair forces go to per-pair slots; every owner adds its own slots by following a chain in append
-//              order = canonical neighbour order, so the sum is bit-identical to the sequential one.
+//              Every owner's pairs take one contiguous list segment (offsets from a warp scan of the per-lane
+//              counts) in canonical neighbour order; pair forces go to per-pair slots and every owner adds its own
+//              segment front to back, so the sum is bit-identical to the sequential one.
 //
 // Agents whose stencil has more than 3 columns (eyesight > cell size) or a slice with more than 32 candidates are
 // put on a device-side list and finished by step_slow_kernel with the sequential routine.  Same arithmetic, same
@@ -32,7 +33,8 @@
 namespace rcs {
 
 constexpr int SW_WARPS = 4;            // warps per block
-constexpr int SW_LIST = 96;            // entries per pair list; flushed when more than SW_LIST - 32 are queued
+constexpr int SW_LIST = 96;            // stage-2 hit list; flushed when more than SW_LIST - 32 pairs are queued
+constexpr uint32_t SW_CAP = 128;       // stage-3 pair lists (A: evaluate, B: prove zero); >= 3 * SW_SLICE_MAX
 constexpr uint32_t SW_SLICE_MAX = 32;  // candidates per stencil column on the cooperative path (mask width)
 constexpr uint32_t SW_NONE = 0xffffu;
 
@@ -42,12 +44,11 @@ struct WarpShared {
   double futx[32], futy[32], mag[32], mvx[32], mvy[32], f0x[32], f0y[32];     // OwnerPre (stage 3)
   unsigned long long id[32];
   unsigned long long tbits[32];
-  double sfx[SW_LIST], sfy[SW_LIST];   // pair forces of list A
-  uint32_t lj[2 * SW_LIST];            // neighbour slot: list A (and the stage-2 hit list) | list B
+  double sfx[SW_CAP], sfy[SW_CAP];     // pair forces of list A
+  uint32_t lj[2 * SW_CAP];             // neighbour slot: list A (and the stage-2 hit list) | list B
   uint32_t grp[32];
   unsigned int poison[32];
-  uint16_t nxt[SW_LIST];               // per-owner chain through list A
-  uint8_t lo[2 * SW_LIST];             // owner lane: list A | list B
+  uint8_t lo[2 * SW_CAP];              // owner lane: list A | list B
 };
 
 __global__ void __launch_bounds__(32 * SW_WARPS, 5) step_warp_kernel(StepArgs a) {
@@ -184,25 +185,30 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 5) step_warp_kernel(StepArgs a)
         __syncwarp();
         cnt = 0;
       };
-      uint32_t b0 = m0, b1 = m1, b2 = m2;
-      while (__any_sync(FULL, (b0 | b1 | b2) != 0u)) {
+      // (word, slice start) queue of this lane; empty words are popped with predicated moves, so the walk over
+      // the three slices stays free of divergent branches
+      uint32_t bits = m0, base = s0, nb1 = m1, ns1 = s1, nb2 = m2, ns2 = s2, k = 0;
+      while (__any_sync(FULL, (bits | nb1 | nb2) != 0u)) {
         bool hit = false;
         uint32_t j = 0;
-        if ((b0 | b1 | b2) != 0u) {
-          uint32_t t, k;
-          if (b0) {
-            t = __ffs(b0) - 1; b0 &= b0 - 1u; j = s0 + t; k = 0;
-          } else if (b1) {
-            t = __ffs(b1) - 1; b1 &= b1 - 1u; j = s1 + t; k = 1;
-          } else {
-            t = __ffs(b2) - 1; b2 &= b2 - 1u; j = s2 + t; k = 2;
-          }
-          if (me.id < ids[j]) {
-            const uint32_t bit = 1u << t;
-            if (k == 0) y0 |= bit;
-            else if (k == 1) y1 |= bit;
-            else y2 |= bit;
-          }
+#pragma unroll
+        for (int pop = 0; pop < 2; ++pop) {
+          const bool empty = bits == 0u;
+          bits = empty ? nb1 : bits;
+          base = empty ? ns1 : base;
+          nb1 = empty ? nb2 : nb1;
+          ns1 = empty ? ns2 : ns1;
+          nb2 = empty ? 0u : nb2;
+          k += empty ? 1u : 0u;
+        }
+        if (bits != 0u) {
+          const uint32_t t = __ffs(bits) - 1;
+          bits &= bits - 1u;
+          j = base + t;
+          const uint32_t bit = (me.id < ids[j]) ? (1u << t) : 0u;
+          y0 |= (k == 0u) ? bit : 0u;
+          y1 |= (k == 1u) ? bit : 0u;
+          y2 |= (k == 2u) ? bit : 0u;
           // the division-free half of time_to_collision; same operations as rcs_math.cuh
           const double dx = xs[j] - me.px;
           const double dy = ys[j] - me.py;
@@ -260,8 +266,6 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 5) step_warp_kernel(StepArgs a)
         z0 = m0 & ~y0; z1 = m1 & ~y1; z2 = m2 & ~y2;
       }
       __syncwarp();
-      uint32_t cntA = 0, cntB = 0;
-      uint32_t first = SW_NONE, last = SW_NONE;
       auto load_pre = [&](uint32_t o) {
         OwnerPre p;
         p.futx = w.futx[o]; p.futy = w.futy[o]; p.mag = w.mag[o];
@@ -275,9 +279,42 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 5) step_warp_kernel(StepArgs a)
         p.ox = xs[j]; p.oy = ys[j]; p.ovx = vxs[j]; p.ovy = vys[j]; p.oid = ids[j];
         pair_force_literal(p, w.ti[o], a.groups[w.grp[o]], qx, qy);
       };
-      auto flush_A = [&]() {
+      // Every owner's pairs take one contiguous segment of a list, in canonical neighbour order (slice 0, 1, 2;
+      // ascending slot), so the owner later adds its own slots front to back.  Segment offsets come from one warp
+      // scan of the per-lane counts (list A in the low half-word, list B in the high one).
+      const uint32_t cA = __popc(a0) + __popc(a1) + __popc(a2);
+      const uint32_t cB = __popc(z0) + __popc(z1) + __popc(z2);
+      const uint32_t own_cnt = cA | (cB << 16);
+      uint32_t inc = own_cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, inc, d);
+        if (lane >= (unsigned)d) inc += t;
+      }
+      const uint32_t exc = inc - own_cnt;
+      uint32_t lane_begin = 0;
+      while (lane_begin < 32) {  // one round unless the warp holds more pairs than a list does
+        const uint32_t base = __shfl_sync(FULL, exc, lane_begin);
+        const uint32_t rel = exc - base;  // field-wise: prefix sums are monotone, no borrow between the halves
+        const uint32_t offA = rel & 0xffffu, offB = rel >> 16;
+        const bool fits = lane >= lane_begin && offA + cA <= SW_CAP && offB + cB <= SW_CAP;
+        const unsigned okm = __ballot_sync(FULL, fits || lane < lane_begin);
+        const uint32_t lane_end = (okm == FULL) ? 32u : (uint32_t)(__ffs(~okm) - 1);  // > lane_begin: cA, cB <= 96
+        const bool part = lane >= lane_begin && lane < lane_end;
+        if (part) {
+          uint32_t p = offA;
+          for (uint32_t bits = a0; bits; bits &= bits - 1u) { w.lj[p] = s0 + __ffs(bits) - 1; w.lo[p] = (uint8_t)lane; ++p; }
+          for (uint32_t bits = a1; bits; bits &= bits - 1u) { w.lj[p] = s1 + __ffs(bits) - 1; w.lo[p] = (uint8_t)lane; ++p; }
+          for (uint32_t bits = a2; bits; bits &= bits - 1u) { w.lj[p] = s2 + __ffs(bits) - 1; w.lo[p] = (uint8_t)lane; ++p; }
+          p = SW_CAP + offB;
+          for (uint32_t bits = z0; bits; bits &= bits - 1u) { w.lj[p] = s0 + __ffs(bits) - 1; w.lo[p] = (uint8_t)lane; ++p; }
+          for (uint32_t bits = z1; bits; bits &= bits - 1u) { w.lj[p] = s1 + __ffs(bits) - 1; w.lo[p] = (uint8_t)lane; ++p; }
+          for (uint32_t bits = z2; bits; bits &= bits - 1u) { w.lj[p] = s2 + __ffs(bits) - 1; w.lo[p] = (uint8_t)lane; ++p; }
+        }
+        const uint32_t tot = __shfl_sync(FULL, inc, lane_end - 1) - base;
+        const uint32_t nA = tot & 0xffffu, nB = tot >> 16;
         __syncwarp();
-        for (uint32_t e = lane; e < cntA; e += 32) {
+        for (uint32_t e = lane; e < nA; e += 32) {  // yield pairs: one per lane
           const uint32_t o = w.lo[e];
           const uint32_t j = w.lj[e];
           double qx, qy;
@@ -286,21 +323,9 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 5) step_warp_kernel(StepArgs a)
           w.sfx[e] = qx;
           w.sfy[e] = qy;
         }
-        __syncwarp();
-        // every owner adds its own pairs in append order = canonical neighbour order
-        for (uint32_t e = first; e != SW_NONE; e = w.nxt[e]) {
-          fx = fx + w.sfx[e];
-          fy = fy + w.sfy[e];
-        }
-        first = last = SW_NONE;
-        __syncwarp();
-        cntA = 0;
-      };
-      auto flush_B = [&]() {
-        __syncwarp();
-        for (uint32_t e = lane; e < cntB; e += 32) {
-          const uint32_t o = w.lo[SW_LIST + e];
-          const uint32_t j = w.lj[SW_LIST + e];
+        for (uint32_t e = lane; e < nB; e += 32) {  // weight-0 pairs: prove the contribution is (+-0, +-0)
+          const uint32_t o = w.lo[SW_CAP + e];
+          const uint32_t j = w.lj[SW_CAP + e];
           if (!pair_force_w0_is_zero(load_pre(o), xs[j], ys[j], vxs[j], vys[j], w.ti[o])) {
             // contributes NaN or +-0 per component (rcs_math.cuh): NaN is order-independent
             double qx, qy;
@@ -310,49 +335,15 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 5) step_warp_kernel(StepArgs a)
           }
         }
         __syncwarp();
-        cntB = 0;
-      };
-      while (__any_sync(FULL, (a0 | a1 | a2 | z0 | z1 | z2) != 0u)) {
-        // one list-A and one list-B pair per lane and iteration
-        bool passA = false, passB = false;
-        uint32_t jA = 0, jB = 0;
-        if (a0) {
-          jA = s0 + __ffs(a0) - 1; a0 &= a0 - 1u; passA = true;
-        } else if (a1) {
-          jA = s1 + __ffs(a1) - 1; a1 &= a1 - 1u; passA = true;
-        } else if (a2) {
-          jA = s2 + __ffs(a2) - 1; a2 &= a2 - 1u; passA = true;
+        if (part) {
+          for (uint32_t r = 0; r < cA; ++r) {
+            fx = fx + w.sfx[offA + r];
+            fy = fy + w.sfy[offA + r];
+          }
         }
-        if (z0) {
-          jB = s0 + __ffs(z0) - 1; z0 &= z0 - 1u; passB = true;
-        } else if (z1) {
-          jB = s1 + __ffs(z1) - 1; z1 &= z1 - 1u; passB = true;
-        } else if (z2) {
-          jB = s2 + __ffs(z2) - 1; z2 &= z2 - 1u; passB = true;
-        }
-        const unsigned mA = __ballot_sync(FULL, passA);
-        const unsigned mB = __ballot_sync(FULL, passB);
-        if (passA) {
-          const uint32_t pos = cntA + __popc(mA & lt_mask);
-          w.lj[pos] = jA;
-          w.lo[pos] = (uint8_t)lane;
-          w.nxt[pos] = (uint16_t)SW_NONE;
-          if (last != SW_NONE) w.nxt[last] = (uint16_t)pos;
-          else first = pos;
-          last = pos;
-        }
-        if (passB) {
-          const uint32_t pos = SW_LIST + cntB + __popc(mB & lt_mask);
-          w.lj[pos] = jB;
-          w.lo[pos] = (uint8_t)lane;
-        }
-        cntA += __popc(mA);
-        cntB += __popc(mB);
-        if (cntA > SW_LIST - 32) flush_A();
-        if (cntB > SW_LIST - 32) flush_B();
+        __syncwarp();
+        lane_begin = lane_end;
       }
-      if (cntA) flush_A();
-      if (cntB) flush_B();
       __syncwarp();
       const unsigned pz = w.poison[lane];
       if (pz & 1u) fx = fx + __longlong_as_double(0x7ff8000000000000LL);
