@@ -33,7 +33,6 @@
 namespace rcs {
 
 constexpr int SW_WARPS = 4;            // warps per block
-constexpr int SW_LIST = 96;            // stage-2 hit list; flushed when more than SW_LIST - 32 pairs are queued
 constexpr uint32_t SW_CAP = 128;       // stage-3 pair lists (A: evaluate, B: prove zero); >= 3 * SW_SLICE_MAX
 constexpr uint32_t SW_SLICE_MAX = 32;  // candidates per stencil column on the cooperative path (mask width)
 constexpr uint32_t SW_NONE = 0xffffu;
@@ -48,15 +47,15 @@ struct WarpShared {
   uint32_t lj[2 * SW_CAP];             // neighbour slot: list A (and the stage-2 hit list) | list B
   uint32_t grp[32];
   unsigned int poison[32];
+  uint32_t hcnt;                       // entries in the stage-2 hit list
   uint8_t lo[2 * SW_CAP];              // owner lane: list A | list B
 };
 
-__global__ void __launch_bounds__(32 * SW_WARPS, 5) step_warp_kernel(StepArgs a) {
+__global__ void __launch_bounds__(32 * SW_WARPS, 6) step_warp_kernel(StepArgs a) {
   if (a.status->failed) return;
   __shared__ WarpShared sh[SW_WARPS];
   WarpShared& w = sh[threadIdx.x >> 5];
   const unsigned lane = threadIdx.x & 31u;
-  const unsigned lt_mask = (1u << lane) - 1u;
   const unsigned FULL = 0xffffffffu;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t n_live = *a.n_sorted;
@@ -164,15 +163,16 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 5) step_warp_kernel(StepArgs a)
     w.vy[lane] = me.vy;
     w.rr[lane] = rr;
     w.tbits[lane] = 0x7ff0000000000000ull;
+    if (lane == 0) w.hcnt = 0u;
     __syncwarp();
 
     // ---------------- stage 2: t_i = min over neighbours of time_to_collision (zanlungo.rs:76-91)
     // neighbours with the higher id: this agent yields to them (right_of_way = -1; exact for own ids < 2^53)
     uint32_t y0 = 0, y1 = 0, y2 = 0;
     {
-      uint32_t cnt = 0;
-      auto flush_hits = [&]() {
-        __syncwarp();
+      uint32_t it = 0;
+      auto flush_hits = [&]() {  // entered after a __syncwarp()
+        const uint32_t cnt = *(volatile uint32_t*)&w.hcnt;
         for (uint32_t e = lane; e < cnt; e += 32) {
           const uint32_t o = w.lo[e];
           const uint32_t j = w.lj[e];
@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 5) step_warp_kernel(StepArgs a)
           if (ct < RCS_INF) atomicMin(&w.tbits[o], (unsigned long long)__double_as_longlong(ct));
         }
         __syncwarp();
-        cnt = 0;
+        if (lane == 0) w.hcnt = 0u;
+        __syncwarp();
       };
       // (word, slice start) queue of this lane; empty words are popped with predicated moves, so the walk over
       // the three slices stays free of divergent branches
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 5) step_warp_kernel(StepArgs a)
         bool hit = false;
         uint32_t j = 0;
 #pragma unroll
-        for (int pop = 0; pop < 2; ++pop) {
+        for (int pop = 0; pop < 1; ++pop) {  // one pop per iteration: a lane with two empty words idles once
           const bool empty = bits == 0u;
           bits = empty ? nb1 : bits;
           base = empty ? ns1 : base;
@@ -223,21 +224,23 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 5) step_warp_kernel(StepArgs a)
             const double disc = bb - (4.0 * qa) * qc;
             // A finite time needs disc >= 0 and -b + sqrt(disc) > 0.  For b >= 0, disc <= b*b gives
             // sqrt(disc) <= sqrt(fl(b*b)) = b (correctly rounded sqrt of a square is exact and monotone), so the
-            // numerator is <= 0: INF (b*b overflowing is excluded from the argument).  Everything else is decided
-            // by the literal routine on the compacted list.
-            hit = (disc >= 0.0) && ((qb < 0.0) || (disc > bb) || !(bb < RCS_INF));
+            // numerator is <= 0: INF.  disc == b*b is passed on although it cannot be finite either, so that one
+            // compare also covers b*b = inf.  Everything else is decided by the literal routine on the list.
+            hit = (disc >= 0.0) && ((qb < 0.0) || !(disc < bb));
           }
         }
-        const unsigned hm = __ballot_sync(FULL, hit);
-        if (hit) {
-          const uint32_t pos = cnt + __popc(hm & lt_mask);
+        if (hit) {  // order inside the list is irrelevant (min): a shared counter hands out the slots
+          const uint32_t pos = atomicAdd(&w.hcnt, 1u);
           w.lj[pos] = j;
           w.lo[pos] = (uint8_t)lane;
         }
-        cnt += __popc(hm);
-        if (cnt > SW_LIST - 32) flush_hits();
+        if ((++it & 3u) == 0u) {  // at most 4 x 32 new entries since the last look at the counter
+          __syncwarp();
+          if (*(volatile uint32_t*)&w.hcnt > 2 * SW_CAP - 128) flush_hits();
+        }
       }
-      if (cnt) flush_hits();
+      __syncwarp();
+      if (*(volatile uint32_t*)&w.hcnt) flush_hits();
       __syncwarp();
       if (fast) t_i = __longlong_as_double((long long)w.tbits[lane]);
     }
