@@ -184,7 +184,8 @@ static int upload_counts(rcs_sim* s) {
 static int bin_agents(rcs_sim* s, uint32_t n_ub, const uint32_t* first) {
   if (!n_ub) return RCS_OK;
   bin_count_kernel<<<blocks_for(n_ub, 256), 256, 0, s->stream>>>(s->grid, n_ub, first, s->cnt + CNT_TOT, s->cur.x,
-                                                                 s->cur.y, s->cellid, s->cell_count, s->d_status);
+                                                                 s->cur.y, s->cur_has_dead ? s->keep : nullptr,
+                                                                 s->cellid, s->cell_count, s->d_status);
   s->launches += 1;
   CU_TRY(s, cudaGetLastError());
   return RCS_OK;
@@ -274,19 +275,44 @@ static int drain_kevents(rcs_sim* s) {
 // Undo a failed step on a strip: the snapshot in `cur` (sorted, ghosts included) is reduced to the agents
 // this rank owns.
 static int rollback_owned(rcs_sim* s, uint32_t n_tot) {
-  role_keep_kernel<<<blocks_for(n_tot, 256), 256, 0, s->stream>>>(n_tot, s->cnt + CNT_TOT, s->srt_cell,
-                                                                  (uint32_t)s->grid.nx, s->strip, s->cellid);
+  const uint32_t* n_sorted = s->cell_start + s->grid.len;
+  role_keep_kernel<<<blocks_for(n_tot, 256), 256, 0, s->stream>>>(n_tot, n_sorted, s->srt_cell, (uint32_t)s->grid.nx,
+                                                                  s->strip, s->cellid);
   s->launches += 1;
   int rc = exclusive_scan(s, s->cellid, n_tot, s->perm, nullptr);
   if (rc) return rc;
-  compact_keep_kernel<<<blocks_for(n_tot, 256), 256, 0, s->stream>>>(n_tot, s->cnt + CNT_TOT, s->cellid, s->perm,
-                                                                     s->cur, s->srt, nullptr);
+  compact_keep_kernel<<<blocks_for(n_tot, 256), 256, 0, s->stream>>>(n_tot, n_sorted, s->cellid, s->perm, s->cur,
+                                                                     s->srt, nullptr);
   s->launches += 1;
   uint32_t kept = 0;
   CU_TRY(s, cudaMemcpyAsync(&kept, s->perm + n_tot, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
   CU_TRY(s, cudaStreamSynchronize(s->stream));
   std::swap(s->cur, s->srt);
   s->n = kept;
+  return RCS_OK;
+}
+
+// Drop the entries flagged keep = 0 from `cur` (stream compaction: scan of the flags, then a gather).  Steps do
+// not need this -- the next step's counting sort skips those entries -- so it only runs when the host looks.
+static int compact_cur(rcs_sim* s) {
+  if (!s->cur_has_dead) return RCS_OK;
+  const uint32_t n_ub = s->n;  // entries in cur, dead ones included
+  uint32_t kept = 0;
+  if (n_ub) {
+    int rc = exclusive_scan(s, s->keep, n_ub, s->perm, nullptr);
+    if (rc) return rc;
+    compact_keep_kernel<<<blocks_for(n_ub, 256), 256, 0, s->stream>>>(n_ub, s->cnt + CNT_CUR, s->keep, s->perm, s->cur,
+                                                                      s->srt, nullptr);
+    s->launches += 1;
+    CU_TRY(s, cudaMemcpyAsync(&kept, s->perm + n_ub, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    std::swap(s->cur, s->srt);
+  }
+  s->n = kept;
+  s->n_ub = kept;
+  s->cnt_dirty = true;
+  s->cur_has_dead = false;
+  s->stats.n_agents = kept;
   return RCS_OK;
 }
 
@@ -321,7 +347,9 @@ static int do_sync(rcs_sim* s) {
   if (st.failed) {
     // the step with index k (since the last sync) failed; every later one was skipped on the device
     uint64_t k = steps_done - s->steps_done_at_sync;
-    uint32_t n_snapshot = s->h_cnt[CNT_TOT];
+    // the sorted snapshot of the failed step holds cell_start[len] entries (all live: the sort dropped the rest)
+    uint32_t n_snapshot = 0;
+    CU_TRY(s, cudaMemcpy(&n_snapshot, s->cell_start + s->grid.len, sizeof(uint32_t), cudaMemcpyDeviceToHost));
     if (k < s->pending.size()) {
       const PendingStep& p = s->pending[k];
       if (p.snapshot_in_srt) {
@@ -360,11 +388,13 @@ static int do_sync(rcs_sim* s) {
     }
     s->n_ub = s->n;
     s->cnt_dirty = true;
+    s->cur_has_dead = false;
     s->stats.n_agents = s->n;
     invalidate(s);
   }
   s->pending.clear();
   s->steps_done_at_sync = steps_done;
+  if (rc == RCS_OK && s->cur_has_dead) rc = compact_cur(s);
   return rc;
 }
 

@@ -107,7 +107,7 @@ static StepArgs make_step_args(rcs_sim* s, const AgentArrays& in, const AgentArr
   a.cnt = s->cnt;
   a.slow_list = s->slow_list;
   if (full_out && churn(s)) {
-    a.keep = s->cellid;  // the unsorted cell ids are dead once the agents are gathered into srt
+    a.keep = s->keep;
     a.cell = s->srt_cell;
     a.strip = s->strip;
     if (s->ever_had_sources) {
@@ -139,9 +139,9 @@ static int step_phase_a(rcs_sim* s, double dt) {
     if (n_before)
       ss_probe_kernel<<<blocks_for(n_before, 256), 256, 0, s->stream>>>(
           s->grid, s->sgrid, s->d_sources, radius_threshold(0.4), n_before, s->cnt + CNT_CUR, s->cur.x, s->cur.y,
-          s->d_blocked, s->d_status);
+          s->cur_has_dead ? s->keep : nullptr, s->d_blocked, s->d_status);
     ss_spawn_kernel<<<1, SCAN_THREADS, 0, s->stream>>>(s->grid, s->d_sources, (uint32_t)s->sources.size(), dt,
-                                                       s->d_blocked, s->cur, (uint32_t)s->cap, s->cnt, s->d_next_id,
+                                                       s->d_blocked, s->cur, s->keep, (uint32_t)s->cap, s->cnt, s->d_next_id,
                                                        s->ev_spawn_id, s->ev_spawn_xy, s->ev_cap, s->d_status);
     s->launches += 2;
     s->n_ub = (uint32_t)std::min<uint64_t>(s->cap, (uint64_t)s->n_ub + s->n_sources_alive);
@@ -192,12 +192,13 @@ static int step_phase_b(rcs_sim* s, double dt, uint32_t flags) {
   const uint32_t n_ub = s->n_ub;
   PendingStep p{s->cur, s->srt, true, s->n};
   int rc = RCS_OK;
+  bool churned = false;
   if (n_ub && sorted_path(s)) {
     if (s->strip.enabled) {
       const int has_l = s->rank > 0, has_r = s->rank + 1 < s->world;
       const uint32_t ghosts_ub = s->recv_l.buf.cap + s->recv_r.buf.cap;
       halo_unpack_kernel<<<blocks_for(ghosts_ub, 256), 256, 0, s->stream>>>(
-          s->cur, (uint32_t)s->cap, s->recv_l.buf, s->recv_r.buf, has_l, has_r, s->cnt, s->d_status);
+          s->cur, s->keep, (uint32_t)s->cap, s->recv_l.buf, s->recv_r.buf, has_l, has_r, s->cnt, s->d_status);
       s->launches += 1;
       rc = bin_agents(s, n_ub, s->cnt + CNT_CUR);
     } else {
@@ -239,18 +240,11 @@ static int step_phase_b(rcs_sim* s, double dt, uint32_t flags) {
       s->tr_n = std::min(n_sorted, n_ub);
     }
     if (churn(s)) {
-      rc = exclusive_scan(s, s->cellid, n_ub, s->perm, nullptr);
-      if (rc) return rc;
-      if (no_commit) {
-        compact_keep_kernel<<<blocks_for(n_ub, 256), 256, 0, s->stream>>>(n_ub, a.n_sorted, s->cellid, s->perm, s->srt,
-                                                                          s->cur, s->d_status);
-      } else {
-        compact_keep_kernel<<<blocks_for(n_ub, 256), 256, 0, s->stream>>>(n_ub, a.n_sorted, s->cellid, s->perm, s->cur,
-                                                                          s->srt, s->d_status);
-        std::swap(s->cur, s->srt);
-      }
-      set_count_kernel<<<1, 1, 0, s->stream>>>(s->cnt + CNT_CUR, s->perm + n_ub, s->d_status);
-      s->launches += 2;
+      // The new state (or, without commit, the sorted snapshot) holds the agents that stay AND the ones that
+      // leave, told apart by the keep flags the step kernel wrote.  Nothing is moved: the next step's counting
+      // sort skips the flagged entries, and rcs_sync compacts when the host wants to look (compact_cur).
+      if (no_commit) std::swap(s->cur, s->srt);
+      churned = true;
     } else if (no_commit) {
       std::swap(s->cur, s->srt);  // the sorted pre-step snapshot becomes current again
     }
@@ -270,9 +264,11 @@ static int step_phase_b(rcs_sim* s, double dt, uint32_t flags) {
       std::swap(s->cur.vy, s->srt.vy);
     }
   }
-  end_step_kernel<<<1, 1, 0, s->stream>>>(s->d_status, s->d_steps_done);
+  end_step_kernel<<<1, 1, 0, s->stream>>>(s->d_status, s->d_steps_done, churned ? s->cnt + CNT_CUR : nullptr,
+                                          s->cell_start + s->grid.len);
   s->launches += 1;
   CU_TRY(s, cudaGetLastError());
+  if (churned) s->cur_has_dead = true;
   s->pending.push_back(p);
   s->steps_enqueued += 1;
   s->index_valid = false;

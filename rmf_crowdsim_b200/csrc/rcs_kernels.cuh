@@ -71,14 +71,20 @@ constexpr uint32_t CELL_DEAD = 0xffffffffu;
 // ---------------------------------------------------------------------------------------------
 // A1/A2: cell of every agent (LocationHash2D::location_to_index) + histogram.
 // ---------------------------------------------------------------------------------------------
-// Agents [*first (0 if null), min(n_ub, *last)) of the unsorted arrays.
+// Agents [*first (0 if null), min(n_ub, *last)) of the unsorted arrays.  Entries whose keep flag is 0 (despawned
+// at a sink, migrated to another strip, ghosts of the previous step) are dropped here: the counting sort of the
+// next step is the stream compaction.
 __global__ void bin_count_kernel(GridDev g, uint32_t n_ub, const uint32_t* __restrict__ first,
                                  const uint32_t* __restrict__ last, const double* __restrict__ x,
-                                 const double* __restrict__ y, uint32_t* __restrict__ cellid,
-                                 uint32_t* __restrict__ cell_count, DevStatus* status) {
+                                 const double* __restrict__ y, const uint32_t* __restrict__ keep,
+                                 uint32_t* __restrict__ cellid, uint32_t* __restrict__ cell_count, DevStatus* status) {
   if (status->failed) return;
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x + (first ? *first : 0u);
   if (i >= n_ub || i >= *last) return;
+  if (keep && !keep[i]) {
+    cellid[i] = CELL_DEAD;
+    return;
+  }
   uint64_t idx;
   if (location_to_index(g, x[i], y[i], idx)) {
     cellid[i] = (uint32_t)idx;
@@ -894,8 +900,11 @@ __global__ void verdict_kernel(DevStatus* st, int oob_fails) {
   }
 }
 
-__global__ void end_step_kernel(DevStatus* st, unsigned long long* steps_done) {
+// cnt_cur != nullptr on steps with churn: the state now holds *n_sorted entries (some flagged keep = 0)
+__global__ void end_step_kernel(DevStatus* st, unsigned long long* steps_done, uint32_t* cnt_cur,
+                                const uint32_t* n_sorted) {
   if (st->failed) return;
+  if (cnt_cur) *cnt_cur = *n_sorted;
   *steps_done += 1;
 }
 
@@ -954,11 +963,12 @@ struct SourceGridDev {
 
 __global__ void ss_probe_kernel(GridDev g, SourceGridDev sg, const SourceSinkDev* __restrict__ ss, double thr2_probe,
                                 uint32_t n_ub, const uint32_t* __restrict__ n_ptr, const double* __restrict__ x,
-                                const double* __restrict__ y, uint32_t* __restrict__ blocked,
-                                const DevStatus* status) {
+                                const double* __restrict__ y, const uint32_t* __restrict__ keep,
+                                uint32_t* __restrict__ blocked, const DevStatus* status) {
   if (status->failed) return;
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_ub || i >= *n_ptr) return;
+  if (keep && !keep[i]) return;  // removed at the end of the previous step (lib.rs:378-380)
   const double px = x[i], py = y[i];
   // conservative range of lookup cells around the agent (0.4 m radius + slack)
   const double fx0 = floor((px - 0.45 - sg.x0) / sg.cell), fx1 = floor((px + 0.45 - sg.x0) / sg.cell);
@@ -993,8 +1003,8 @@ __global__ void ss_probe_kernel(GridDev g, SourceGridDev sg, const SourceSinkDev
 // generator asks for >= 1 (the reference's loop over spawn_number is commented out, lib.rs:207-219).
 // Ids are allocated sequentially (lib.rs:128-129) in that order.
 __global__ void ss_spawn_kernel(GridDev g, const SourceSinkDev* __restrict__ ss, uint32_t n_ss, double dt,
-                                uint32_t* __restrict__ blocked, AgentArrays cur, uint32_t cap, uint32_t* cnt,
-                                unsigned long long* next_id, unsigned long long* ev_id, double* ev_xy, uint32_t ev_cap,
+                                uint32_t* __restrict__ blocked, AgentArrays cur, uint32_t* __restrict__ keep,
+                                uint32_t cap, uint32_t* cnt, unsigned long long* next_id, unsigned long long* ev_id, double* ev_xy, uint32_t ev_cap,
                                 DevStatus* status) {
   if (status->failed) return;
   __shared__ uint32_t base;
@@ -1027,6 +1037,7 @@ __global__ void ss_spawn_kernel(GridDev g, const SourceSinkDev* __restrict__ ss,
         cur.id[slot] = id0 + off + rank;
         cur.grp[slot] = s.grp;
         cur.wp[slot] = 0u;
+        keep[slot] = 1u;
         if (cur.pvx) {
           cur.pvx[slot] = __longlong_as_double(0x7ff8000000000000LL);
           cur.pvy[slot] = __longlong_as_double(0x7ff8000000000000LL);
@@ -1111,8 +1122,8 @@ __global__ void halo_header_kernel(HaloBuf left, HaloBuf right, const DevStatus*
 }
 
 // appends the ghosts of both received buffers after the owned agents; cnt[CNT_TOT] = owned + ghosts
-__global__ void halo_unpack_kernel(AgentArrays cur, uint32_t cap, HaloBuf left, HaloBuf right, int has_left,
-                                   int has_right, uint32_t* cnt, DevStatus* status) {
+__global__ void halo_unpack_kernel(AgentArrays cur, uint32_t* __restrict__ keep, uint32_t cap, HaloBuf left,
+                                   HaloBuf right, int has_left, int has_right, uint32_t* cnt, DevStatus* status) {
   if (status->failed) return;
   if ((has_left && left.count[1]) || (has_right && right.count[1])) {
     if (blockIdx.x == 0 && threadIdx.x == 0) status->failed = 1;  // a neighbour failed: stop here too
@@ -1143,6 +1154,7 @@ __global__ void halo_unpack_kernel(AgentArrays cur, uint32_t cap, HaloBuf left, 
   cur.id[slot] = b.id[e];
   cur.grp[slot] = (uint32_t)(b.meta[e] & 0xffffffffull);
   cur.wp[slot] = (uint32_t)(b.meta[e] >> 32);
+  keep[slot] = 1u;
   if (cur.pvx) {
     cur.pvx[slot] = b.pvx[e];
     cur.pvy[slot] = b.pvy[e];
