@@ -93,12 +93,22 @@ int rcs_lp_zanlungo(rcs_sim* sim, double agent_scale, double obstacle_scale, dou
 /* HighLevelPlanner::get_desired_velocity (highlevel_planners.rs:9) evaluated on the device:
  *  constant: Some(v) for every agent            (fixture of lib.rs:391-420)
  *  parity  : even id -> Some(-v), odd -> Some(v) (fixture of rmf_crowdsim_viz/src/main.rs:20-30)
+ *  route   : rmf::RMFPlanner's waypoint follower on a caller-supplied route (see rcs_hl_route)
  *  host    : Some(table[id]) as uploaded by rcs_set_preferred_velocity, None for ids never set
  *            (slow path that keeps user-implemented HighLevelPlanner trait objects usable)
  *  none    : always None  => velocity (0,0)     (lib.rs:263-273) */
 int rcs_hl_constant(rcs_sim* sim, double vx, double vy, uint32_t* out_hl);
 int rcs_hl_parity(rcs_sim* sim, double vx, double vy, uint32_t* out_hl);
 int rcs_hl_host(rcs_sim* sim, uint32_t* out_hl);
+/* The per-step half of rmf::RMFPlanner (rmf/mod.rs:197-215) on the device: an agent in the planner's
+ * agent_cache heads for point k of the route, advances to k+1 once (position - route[k]).norm() < 1e-1, and
+ * gets Some(normalize(route[k] - position)); agents not in the cache get None.  The route itself is supplied by
+ * the caller (xy = n_points interleaved x,y): the reference plans it with the third-party `mapf` crate
+ * (rmf/mod.rs:160-192), which is host-side graph search and out of scope.  Agents enter the cache at route
+ * point 0 through HighLevelPlanner::set_target: automatically when a SourceSink spawns them (lib.rs:242-249)
+ * and whenever they reach one of its waypoints (lib.rs:326-333), or explicitly with rcs_hl_route_set_target. */
+int rcs_hl_route(rcs_sim* sim, uint64_t n_points, const double* xy, uint32_t* out_hl);
+int rcs_hl_route_set_target(rcs_sim* sim, uint64_t n, const uint64_t* ids);
 int rcs_hl_none(rcs_sim* sim, uint32_t* out_hl);
 
 /* ---- agents ---------------------------------------------------------------------------------- */

@@ -14,6 +14,7 @@ from .sim import (  # noqa: F401
     NoHighLevelPlan,
     NoLocalPlan,
     ParityVelocityPlan,
+    RouteFollowPlan,
     Simulation,
     SourceSink,
     Zanlungo,
@@ -22,5 +23,5 @@ from .sim import (  # noqa: F401
 __all__ = [
     "Agent", "ConstantVelocityPlan", "CrowdGenerator", "CrowdsimError", "Duration", "EventListener",
     "HighLevelPlanner", "LocalPlanner", "LocationHash2D", "MonotonicCrowd", "NoHighLevelPlan", "NoLocalPlan",
-    "ParityVelocityPlan", "Simulation", "SourceSink", "Zanlungo",
+    "ParityVelocityPlan", "RouteFollowPlan", "Simulation", "SourceSink", "Zanlungo",
 ]

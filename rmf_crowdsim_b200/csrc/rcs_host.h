@@ -29,7 +29,7 @@ struct LPDesc {
 struct HLDesc {
   uint32_t kind;
   double vx, vy;
-  uint32_t route;  // HL_ROUTE: index into the route table
+  uint32_t route_off, route_n;  // HL_ROUTE: polyline in the route table
 };
 struct GroupKey {
   uint32_t hl, lp;
@@ -96,6 +96,10 @@ struct rcs_sim {
   std::vector<rcs_host::LPDesc> lps;
   std::vector<rcs_host::HLDesc> hls;
   bool any_zanlungo = false;
+  bool any_route = false;            // an HL_ROUTE group exists: steps take the sorted path (it carries `wp`)
+  std::vector<double> routes;        // route table, interleaved x,y
+  double* d_routes = nullptr;
+  bool routes_dirty = false;
   bool have_host_hl = false;
   rcs::DevStatus* d_status = nullptr;
   rcs::DevStatus* h_status = nullptr;  // pinned

@@ -107,7 +107,7 @@ void rcs_sim_destroy(rcs_sim* s) {
   free_agent_arrays(s->srt);
   cudaFree(s->cellid); cudaFree(s->perm); cudaFree(s->order_by_id); cudaFree(s->cell_count);
   cudaFree(s->cell_start); cudaFree(s->cursor); cudaFree(s->tile_sums); cudaFree(s->scan_total);
-  cudaFree(s->big_list); cudaFree(s->d_groups); cudaFree(s->d_status); cudaFree(s->d_steps_done);
+  cudaFree(s->big_list); cudaFree(s->d_groups); cudaFree(s->d_routes); cudaFree(s->d_status); cudaFree(s->d_steps_done);
   cudaFree(s->d_bad); cudaFree(s->d_bad2); cudaFree(s->slot_of_id); cudaFree(s->id_rank); cudaFree(s->presence);
   cudaFree(s->tr_ti); cudaFree(s->tr_fx); cudaFree(s->tr_fy); cudaFree(s->tr_nbc); cudaFree(s->tr_nbo);
   cudaFree(s->tr_nbids); cudaFree(s->tr_id); cudaFree(s->tr_own); cudaFree(s->stage); cudaFree(s->flush_buf);
@@ -146,13 +146,53 @@ int rcs_lp_zanlungo(rcs_sim* s, double agent_scale, double obstacle_scale, doubl
 
 static int push_hl(rcs_sim* s, uint32_t kind, double vx, double vy, uint32_t* out_hl) {
   if (!s || !out_hl) return RCS_ERR_ARG;
-  s->hls.push_back(HLDesc{kind, vx, vy, 0u});
+  s->hls.push_back(HLDesc{kind, vx, vy, 0u, 0u});
   *out_hl = (uint32_t)s->hls.size() - 1;
   return RCS_OK;
 }
 int rcs_hl_constant(rcs_sim* s, double vx, double vy, uint32_t* out_hl) { return push_hl(s, HL_CONSTANT, vx, vy, out_hl); }
 int rcs_hl_parity(rcs_sim* s, double vx, double vy, uint32_t* out_hl) { return push_hl(s, HL_PARITY, vx, vy, out_hl); }
 int rcs_hl_none(rcs_sim* s, uint32_t* out_hl) { return push_hl(s, HL_NONE, 0, 0, out_hl); }
+int rcs_hl_route(rcs_sim* s, uint64_t n_points, const double* xy, uint32_t* out_hl) {
+  if (!s || !out_hl || !xy || n_points == 0 || n_points > WP_MASK - 1) {
+    if (s) s->err = "a route needs 1..65534 points";
+    return RCS_ERR_ARG;
+  }
+  HLDesc h{HL_ROUTE, 0.0, 0.0, (uint32_t)(s->routes.size() / 2), (uint32_t)n_points};
+  s->routes.insert(s->routes.end(), xy, xy + 2 * n_points);
+  s->routes_dirty = true;
+  s->hls.push_back(h);
+  *out_hl = (uint32_t)s->hls.size() - 1;
+  return RCS_OK;
+}
+
+int rcs_hl_route_set_target(rcs_sim* s, uint64_t m, const uint64_t* ids) {
+  if (!s || (m && !ids)) return RCS_ERR_ARG;
+  if (m == 0) return RCS_OK;
+  CU_TRY(s, cudaSetDevice(s->device));
+  int rc = do_sync(s);
+  if (rc) return rc;
+  rc = build_slot_table(s);
+  if (rc) return rc;
+  rc = ensure_stage(s, m * sizeof(uint64_t));
+  if (rc) return rc;
+  uint64_t* d_ids = static_cast<uint64_t*>(s->stage);
+  CU_TRY(s, cudaMemcpyAsync(d_ids, ids, m * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
+  CU_TRY(s, cudaMemsetAsync(s->d_bad, 0, sizeof(unsigned int), s->stream));
+  route_set_target_kernel<<<blocks_for(m, 256), 256, 0, s->stream>>>((uint32_t)m, d_ids, s->slot_of_id,
+                                                                      std::max<uint64_t>(s->max_id_plus1, 1), s->cur.wp,
+                                                                      s->d_bad);
+  s->launches += 1;
+  unsigned int bad = 0;
+  CU_TRY(s, cudaMemcpyAsync(&bad, s->d_bad, sizeof(bad), cudaMemcpyDeviceToHost, s->stream));
+  CU_TRY(s, cudaStreamSynchronize(s->stream));
+  if (bad) {
+    s->err = "unknown agent id";
+    return RCS_ERR_ARG;
+  }
+  return RCS_OK;
+}
+
 int rcs_hl_host(rcs_sim* s, uint32_t* out_hl) {
   if (!s || !out_hl) return RCS_ERR_ARG;
   CU_TRY(s, cudaSetDevice(s->device));
@@ -479,6 +519,8 @@ int rcs_read_agents(rcs_sim* s, uint32_t order, uint64_t cap, uint64_t* ids, dou
     if (next_waypoint) { rc = read_array<uint32_t>(s, s->cur.wp, ord, n, next_waypoint, off); if (rc) return rc; }
   }
   CU_TRY(s, cudaStreamSynchronize(s->stream));
+  if (next_waypoint && s->any_route)  // the high half of the word is the route follower's cache entry
+    for (uint32_t k = 0; k < n; ++k) next_waypoint[k] &= WP_MASK;
   return RCS_OK;
 }
 

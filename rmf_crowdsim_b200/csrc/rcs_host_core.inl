@@ -127,6 +127,9 @@ static uint32_t find_or_add_group(rcs_sim* s, uint32_t hl, uint32_t lp, double e
   g.hl_vx = H.vx;
   g.hl_vy = H.vy;
   g.hl_kind = H.kind;
+  g.route_off = H.route_off;
+  g.route_n = H.route_n;
+  if (H.kind == HL_ROUTE) s->any_route = true;
   g.lp_kind = L.kind;
   g.source_sink = source_sink;
   if (L.kind == LP_ZANLUNGO) {
@@ -246,7 +249,7 @@ static void launch_step_kernel(rcs_sim* s, const StepArgs& a, uint32_t n_ub, boo
   if (sorted_input && s->opt_step_kernel != 1) {
     step_warp_kernel<<<blocks_for(n_ub, 32 * SW_WARPS), 32 * SW_WARPS, 0, s->stream>>>(a);
     // agents with a stencil wider than three columns or very crowded cells (device-side list)
-    step_slow_kernel<<<148 * 4, 128, 0, s->stream>>>(a);
+    step_slow_kernel<<<148 * 2, 128, 0, s->stream>>>(a);
     s->launches += 2;
   } else {
     step_kernel<<<blocks_for(n_ub, 128), 128, 0, s->stream>>>(a);

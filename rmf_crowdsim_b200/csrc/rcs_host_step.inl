@@ -10,9 +10,9 @@
 //   phase B   halo unpack + bin ghosts      [strips]  ghosts appended behind the owned agents
 //             bin -> scan -> scatter -> sort cells by id -> gather      LocationHash2D rebuild (A1, A2)
 //             step_warp (+ step_slow)                 radius query + Zanlungo + Euler (A3-A11), keep flags (A12)
-//             verdict                                 out of bounds / halo / capacity => the step does not stand
-//             scan(keep) + compact          [churn]   despawn at sinks, strip ownership
-//             end_step
+//             end_step                                out of bounds / halo / capacity => the step does not stand;
+//                                                     [churn] leaving agents are only FLAGGED (keep = 0): the next
+//                                                     step's counting sort drops them, rcs_sync compacts on demand
 //
 // NoLocalPlan-only crowds without churn skip the index: the step is one streaming kernel in storage order.
 
@@ -106,6 +106,8 @@ static StepArgs make_step_args(rcs_sim* s, const AgentArrays& in, const AgentArr
   }
   a.cnt = s->cnt;
   a.slow_list = s->slow_list;
+  a.routes = s->d_routes;
+  a.route_thr2 = radius_threshold(1e-1);
   if (full_out && churn(s)) {
     a.keep = s->keep;
     a.cell = s->srt_cell;
@@ -122,11 +124,24 @@ static StepArgs make_step_args(rcs_sim* s, const AgentArrays& in, const AgentArr
 
 static int strip_halo_width(rcs_sim* s);  // rcs_host_dist.inl
 
-static bool sorted_path(const rcs_sim* s) { return s->any_zanlungo || s->trace || churn(s); }
+static bool sorted_path(const rcs_sim* s) { return s->any_zanlungo || s->any_route || s->trace || churn(s); }
 
 // ---- phase A ------------------------------------------------------------------------------------
+static int upload_routes(rcs_sim* s) {
+  if (!s->routes_dirty) return RCS_OK;
+  CU_TRY(s, cudaStreamSynchronize(s->stream));
+  cudaFree(s->d_routes);
+  s->d_routes = nullptr;
+  CU_TRY(s, dalloc(&s->d_routes, s->routes.size()));
+  CU_TRY(s, cudaMemcpy(s->d_routes, s->routes.data(), s->routes.size() * sizeof(double), cudaMemcpyHostToDevice));
+  s->routes_dirty = false;
+  return RCS_OK;
+}
+
 static int step_phase_a(rcs_sim* s, double dt) {
   int rc = upload_groups(s);
+  if (rc) return rc;
+  rc = upload_routes(s);
   if (rc) return rc;
   rc = upload_sources(s);
   if (rc) return rc;
@@ -140,7 +155,7 @@ static int step_phase_a(rcs_sim* s, double dt) {
       ss_probe_kernel<<<blocks_for(n_before, 256), 256, 0, s->stream>>>(
           s->grid, s->sgrid, s->d_sources, radius_threshold(0.4), n_before, s->cnt + CNT_CUR, s->cur.x, s->cur.y,
           s->cur_has_dead ? s->keep : nullptr, s->d_blocked, s->d_status);
-    ss_spawn_kernel<<<1, SCAN_THREADS, 0, s->stream>>>(s->grid, s->d_sources, (uint32_t)s->sources.size(), dt,
+    ss_spawn_kernel<<<1, SCAN_THREADS, 0, s->stream>>>(s->grid, s->d_sources, s->d_groups, (uint32_t)s->sources.size(), dt,
                                                        s->d_blocked, s->cur, s->keep, (uint32_t)s->cap, s->cnt, s->d_next_id,
                                                        s->ev_spawn_id, s->ev_spawn_xy, s->ev_cap, s->d_status);
     s->launches += 2;
@@ -214,8 +229,6 @@ static int step_phase_b(rcs_sim* s, double dt, uint32_t flags) {
     }
     StepArgs a = make_step_args(s, s->srt, s->cur, dt, n_ub, true, flags);
     launch_step_kernel(s, a, n_ub, true);
-    verdict_kernel<<<1, 1, 0, s->stream>>>(s->d_status, no_commit ? 0 : 1);
-    s->launches += 1;
     CU_TRY(s, cudaGetLastError());
     if (s->trace) {
       // neighbour lists of this step (debug path: synchronous), read from the sorted snapshot in srt
@@ -254,8 +267,6 @@ static int step_phase_b(rcs_sim* s, double dt, uint32_t flags) {
     StepArgs a = make_step_args(s, s->cur, s->srt, dt, n_ub, false, flags);
     a.n_sorted = s->cnt + CNT_CUR;
     launch_step_kernel(s, a, n_ub, false);
-    verdict_kernel<<<1, 1, 0, s->stream>>>(s->d_status, no_commit ? 0 : 1);
-    s->launches += 1;
     p.snapshot_in_srt = false;
     if (!no_commit) {
       std::swap(s->cur.x, s->srt.x);
@@ -264,8 +275,8 @@ static int step_phase_b(rcs_sim* s, double dt, uint32_t flags) {
       std::swap(s->cur.vy, s->srt.vy);
     }
   }
-  end_step_kernel<<<1, 1, 0, s->stream>>>(s->d_status, s->d_steps_done, churned ? s->cnt + CNT_CUR : nullptr,
-                                          s->cell_start + s->grid.len);
+  end_step_kernel<<<1, 1, 0, s->stream>>>(s->d_status, no_commit ? 0 : 1, s->d_steps_done,
+                                          churned ? s->cnt + CNT_CUR : nullptr, s->cell_start + s->grid.len);
   s->launches += 1;
   CU_TRY(s, cudaGetLastError());
   if (churned) s->cur_has_dead = true;
@@ -324,6 +335,10 @@ int rcs_add_source_sink(rcs_sim* s, const rcs_source_sink_desc* d, uint64_t* out
   CU_TRY(s, cudaSetDevice(s->device));
   if (d->hl >= s->hls.size() || d->lp >= s->lps.size()) {
     s->err = "unknown planner handle";
+    return RCS_ERR_ARG;
+  }
+  if (d->n_waypoints > WP_MASK) {
+    s->err = "a source sink can have at most 65535 waypoints";
     return RCS_ERR_ARG;
   }
   if (d->n_waypoints == 0 || !d->waypoints_xy) {

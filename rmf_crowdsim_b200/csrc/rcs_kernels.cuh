@@ -353,7 +353,14 @@ struct StepArgs {
   unsigned long long* ev_destroyed;  // (id, step) pairs of agents removed at sinks
   uint32_t ev_cap;
   uint32_t* slow_list;             // warp kernel: agents left to the sequential kernel
+  const double* routes;            // HL_ROUTE polylines, interleaved x,y
+  double route_thr2;               // smallest double T with sqrt(T) >= 1e-1 (rmf/mod.rs:202)
 };
+
+// next_waypoint (lib.rs:61) lives in the low half of the per-agent `wp` word; the high half is the agent's entry
+// in the route follower's agent_cache (rmf/mod.rs:86): 0 = absent, k + 1 = heading for route point k.
+constexpr uint32_t WP_MASK = 0xffffu;
+constexpr int WP_ROUTE_SHIFT = 16;
 
 enum : uint32_t { ROLE_PASSIVE = 0, ROLE_OWN = 1, ROLE_RING = 2 };
 
@@ -370,6 +377,7 @@ __device__ __forceinline__ uint32_t agent_role(const StepArgs& a, uint32_t i) {
 struct Self {
   double px, py, vx, vy, pfx, pfy;
   uint64_t id;
+  uint32_t rwp;  // route follower entry after this step's get_desired_velocity (HL_ROUTE only)
 };
 
 // Walks the reference's radius query for one agent and calls f(j) for every neighbour j that
@@ -467,6 +475,27 @@ __device__ __forceinline__ void high_level_velocity(const StepArgs& a, uint32_t 
       me.pfx = velx;
       me.pfy = vely;
       break;
+    case HL_ROUTE: {
+      // the per-step half of RMFPlanner::get_desired_velocity (rmf/mod.rs:197-215) on a caller-supplied route
+      uint32_t rw = a.in.wp[i] >> WP_ROUTE_SHIFT;
+      if (rw != 0u) {  // in agent_cache
+        uint32_t wid = rw - 1u;
+        const double* r = a.routes + 2 * (size_t)g.route_off;
+        double dx = me.px - r[2 * wid], dy = me.py - r[2 * wid + 1];
+        if (dx * dx + dy * dy < a.route_thr2 && g.route_n > wid + 1u) {  // (pos - route[wp]).norm() < 1e-1
+          wid += 1u;
+          rw += 1u;
+        }
+        dx = r[2 * wid] - me.px;
+        dy = r[2 * wid + 1] - me.py;
+        const double nrm = sqrt(dx * dx + dy * dy);
+        velx = dx / nrm;  // normalize(): component-wise division by the norm
+        vely = dy / nrm;
+        me.pfx = velx;
+        me.pfy = vely;
+      }
+      me.rwp = rw;
+    } break;
     case HL_HOST: {
       double hx = a.in.pvx[i], hy = a.in.pvy[i];
       if (hx == hx) {  // NaN in x encodes None
@@ -513,7 +542,9 @@ __device__ __forceinline__ void integrate_and_store(const StepArgs& a, uint32_t 
   if (own && !(isfinite(nx) && isfinite(ny) && isfinite(velx) && isfinite(vely)))
     atomicAdd(&a.status->nonfinite_count, 1u);
   if (!a.oid) return;  // streaming path: x,y,vx,vy only
-  uint32_t wp = a.in.wp[i];
+  const uint32_t wp_in = a.in.wp[i];
+  uint32_t wp = wp_in & WP_MASK;
+  uint32_t rwp = g.hl_kind == HL_ROUTE ? me.rwp : (wp_in >> WP_ROUTE_SHIFT);
   bool keep = true;
   if (a.ss && g.source_sink >= 0) {
     const SourceSinkDev& ss = a.ss[g.source_sink];
@@ -539,13 +570,16 @@ __device__ __forceinline__ void integrate_and_store(const StepArgs& a, uint32_t 
           }
         } else {
           wp += 1;
+          // HighLevelPlanner::set_target(.., waypoints[next_waypoint], ..) (lib.rs:326-333): the route follower
+          // starts over at the head of its route (rmf/mod.rs:217-237 inserts (route, 0))
+          if (g.hl_kind == HL_ROUTE) rwp = 1u;
         }
       }
     }
   }
   a.oid[i] = me.id;
   a.ogrp[i] = grp;
-  a.owp[i] = wp;
+  a.owp[i] = wp | (rwp << WP_ROUTE_SHIFT);
   if (a.opvx) {
     a.opvx[i] = a.in.pvx[i];
     a.opvy[i] = a.in.pvy[i];
@@ -599,6 +633,7 @@ __device__ __forceinline__ void step_one_agent(const StepArgs& a, uint32_t i, ui
   me.vx = a.in.vx[i];
   me.vy = a.in.vy[i];
   me.id = a.in.id[i];
+  me.rwp = 0u;
   double velx, vely;
   high_level_velocity(a, i, g, me, velx, vely);
   double t_i = RCS_INF, fx = 0.0, fy = 0.0;
@@ -857,6 +892,26 @@ __global__ void scatter_by_id_kernel(uint32_t n, const uint32_t* __restrict__ or
   dst[s] = src[(size_t)k * src_stride];
 }
 
+// RMFPlanner::set_target for agents addressed by id: (route, 0) into the agent_cache (rmf/mod.rs:217-237)
+__global__ void route_set_target_kernel(uint32_t m, const uint64_t* __restrict__ ids,
+                                        const uint32_t* __restrict__ slot_of_id, uint64_t table_len,
+                                        uint32_t* __restrict__ wp, unsigned int* bad) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m) return;
+  uint64_t v = ids[k];
+  uint32_t sl = v < table_len ? slot_of_id[v] : 0xffffffffu;
+  if (sl == 0xffffffffu) {
+    atomicAdd(bad, 1u);
+    return;
+  }
+  wp[sl] = (wp[sl] & WP_MASK) | (1u << WP_ROUTE_SHIFT);
+}
+
+__global__ void mask_u32_kernel(uint64_t n, uint32_t* p, uint32_t mask) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] &= mask;
+}
+
 __global__ void fill_u32_kernel(uint64_t n, uint32_t* p, uint32_t v) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -891,19 +946,17 @@ __global__ void begin_step_kernel(DevStatus* st, uint32_t* cnt) {
   cnt[CNT_EV_DESTROY_SAVE] = cnt[CNT_EV_DESTROY];
 }
 
-// after the step kernels, before anything is committed: does this step stand?
-__global__ void verdict_kernel(DevStatus* st, int oob_fails) {
+// Last kernel of a step: does the step stand?  (Out of bounds only fails committed steps.)  A failing step sets
+// the sticky flag; nothing has been moved yet -- the pre-step snapshot is still intact for rcs_sync to restore.
+// cnt_cur != nullptr on steps with churn: the state now holds *n_sorted entries (some flagged keep = 0).
+__global__ void end_step_kernel(DevStatus* st, int oob_fails, unsigned long long* steps_done, uint32_t* cnt_cur,
+                                const uint32_t* n_sorted) {
   if (st->failed) return;
   if ((oob_fails && st->oob_count) || st->halo_err || st->capacity_err) {
     st->local_failed = 1;
     st->failed = 1;
+    return;
   }
-}
-
-// cnt_cur != nullptr on steps with churn: the state now holds *n_sorted entries (some flagged keep = 0)
-__global__ void end_step_kernel(DevStatus* st, unsigned long long* steps_done, uint32_t* cnt_cur,
-                                const uint32_t* n_sorted) {
-  if (st->failed) return;
   if (cnt_cur) *cnt_cur = *n_sorted;
   *steps_done += 1;
 }
@@ -1002,7 +1055,8 @@ __global__ void ss_probe_kernel(GridDev g, SourceGridDev sg, const SourceSinkDev
 // One block.  Sources in ascending id order; at most ONE agent per source per step and only when the
 // generator asks for >= 1 (the reference's loop over spawn_number is commented out, lib.rs:207-219).
 // Ids are allocated sequentially (lib.rs:128-129) in that order.
-__global__ void ss_spawn_kernel(GridDev g, const SourceSinkDev* __restrict__ ss, uint32_t n_ss, double dt,
+__global__ void ss_spawn_kernel(GridDev g, const SourceSinkDev* __restrict__ ss, const GroupDev* __restrict__ groups,
+                                uint32_t n_ss, double dt,
                                 uint32_t* __restrict__ blocked, AgentArrays cur, uint32_t* __restrict__ keep,
                                 uint32_t cap, uint32_t* cnt, unsigned long long* next_id, unsigned long long* ev_id, double* ev_xy, uint32_t ev_cap,
                                 DevStatus* status) {
@@ -1036,7 +1090,9 @@ __global__ void ss_spawn_kernel(GridDev g, const SourceSinkDev* __restrict__ ss,
         cur.vy[slot] = 0.0;
         cur.id[slot] = id0 + off + rank;
         cur.grp[slot] = s.grp;
-        cur.wp[slot] = 0u;
+        // set_target(agent, waypoints[0], ..) right after the spawn (lib.rs:242-249): a route follower starts at
+        // the head of its route
+        cur.wp[slot] = groups[s.grp].hl_kind == HL_ROUTE ? (1u << WP_ROUTE_SHIFT) : 0u;
         keep[slot] = 1u;
         if (cur.pvx) {
           cur.pvx[slot] = __longlong_as_double(0x7ff8000000000000LL);

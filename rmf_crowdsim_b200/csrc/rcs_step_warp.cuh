@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 6) step_warp_kernel(StepArgs a)
   Self me;
   me.px = me.py = me.vx = me.vy = me.pfx = me.pfy = 0.0;
   me.id = 0;
+  me.rwp = 0u;
   double velx = 0.0, vely = 0.0, thr2 = 0.0, rr = 0.0;
   uint32_t grp = 0, role = ROLE_PASSIVE;
   bool zan = false;

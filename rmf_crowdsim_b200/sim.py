@@ -138,6 +138,18 @@ class ParityVelocityPlan(HighLevelPlanner):
         return (-v[0], -v[1]) if agent.agent_id % 2 == 0 else v
 
 
+class RouteFollowPlan(HighLevelPlanner):
+    """The per-step half of rmf::RMFPlanner (rmf/mod.rs:197-215) on a caller-supplied route, evaluated on the
+    device: head for route[k], advance once within 0.1 m, return the UNIT vector towards it.  Agents enter the
+    planner's cache (at route point 0) when a SourceSink spawns them or sends them to its next waypoint, or
+    through Simulation.route_set_target.  Route planning itself (`mapf` A*) is not part of this library."""
+
+    device_kind = "route"
+
+    def __init__(self, route: Sequence[Vec2f]):
+        self.route = [(float(p[0]), float(p[1])) for p in route]
+
+
 class NoHighLevelPlan(HighLevelPlanner):
     """Always None: velocity (0,0) (lib.rs:263-273)."""
 
@@ -321,6 +333,9 @@ class Simulation:
             N.check(self._h, self._lib.rcs_hl_parity(self._h, hl.default_vel[0], hl.default_vel[1], C.byref(out)))
         elif kind == "none":
             N.check(self._h, self._lib.rcs_hl_none(self._h, C.byref(out)))
+        elif kind == "route":
+            r = _f64(hl.route).reshape(-1)
+            N.check(self._h, self._lib.rcs_hl_route(self._h, len(r) // 2, _p(r, N.c_f64p), C.byref(out)))
         else:
             if self._host_hl_handle is None:
                 N.check(self._h, self._lib.rcs_hl_host(self._h, C.byref(out)))
@@ -473,6 +488,11 @@ class Simulation:
             ids = _u64(ids)
             idp = _p(ids, N.c_u64p)
         N.check(self._h, self._lib.rcs_set_state(self._h, n, idp, *[_p(a, N.c_f64p) for a in arrs]))
+
+    def route_set_target(self, ids) -> None:
+        """HighLevelPlanner::set_target for agents of a RouteFollowPlan: enter the cache at route point 0."""
+        ids = _u64(ids)
+        N.check(self._h, self._lib.rcs_hl_route_set_target(self._h, len(ids), _p(ids, N.c_u64p)))
 
     def set_preferred_velocity(self, ids, vxy) -> None:
         vxy = _f64(vxy).reshape(-1)

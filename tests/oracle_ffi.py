@@ -126,6 +126,10 @@ class OracleSim:
     def hl_host(self):
         return self.L.orc_hl_host(self.h)
 
+    def hl_route(self, route):
+        r = np.ascontiguousarray(route, dtype=np.float64).reshape(-1, 2)
+        return self.L.orc_hl_route(self.h, r.shape[0], _p(r, f64p))
+
     def add_agents(self, xy, hl, lp, eyesight):
         xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
         ids = np.zeros(xy.shape[0], dtype=np.uint64)

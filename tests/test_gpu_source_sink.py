@@ -164,3 +164,48 @@ def test_monotonic_crowd_rounding():
         assert R.MonotonicCrowd(rate).get_number_to_spawn(R.Duration(0, dt_ns)) == expect
         g.step(R.Duration(0, dt_ns))
         assert g.agent_count() == expect
+
+
+def test_route_follower_on_the_device_matches_oracle():
+    """the per-step half of RMFPlanner (rmf/mod.rs:197-215) -- unit velocity towards
+    the current route point, advance within 0.1 m -- with routes supplied as polylines, spawned by source sinks
+    whose coarse waypoints send the agents back to the head of the route (set_target, lib.rs:326-333)."""
+    w = h = 64.0
+    off = (-32.0, -32.0)
+    o = O.OracleSim(w, h, 2.0, off)
+    g = R.Simulation(R.LocationHash2D(w, h, 2.0, off, capacity=2048))
+    keep = []
+    routes = [
+        ((-20.0, -10.0), [(-10.0, -10.0), (-10.0, 0.0), (5.0, 0.0), (20.0, 10.0)], [(-10.0, 0.0), (20.0, 10.0)]),
+        ((20.0, 12.0), [(10.0, 12.0), (0.0, 5.0), (-15.0, 5.0)], [(-15.0, 5.0)]),
+        ((0.0, -25.0), [(0.0, -12.0), (3.0, -2.0), (0.0, 20.0)], [(3.0, -2.0), (0.0, 20.0)]),
+    ]
+    for src, route, wps in routes:
+        o.add_source_sink(src, 0.6, 2.0, o.hl_route(route), o.lp_none(), wps, False, 2.0)
+        hl, lp = R.RouteFollowPlan(route), R.NoLocalPlan()
+        keep.append((hl, lp))
+        g.add_source_sink(R.SourceSink(src, 0.6, R.MonotonicCrowd(2.0), hl, lp, wps, False, 2.0))
+    destroyed = 0
+    for step in range(150):
+        if o.agent_count():
+            P.resync(g, o)
+        g.step(R.Duration(0, 500_000_000))  # unit speed: 0.5 m per step
+        o.step(0, 500_000_000)
+        _, _, d = o.poll_events()
+        destroyed += len(d)
+        assert g.agent_count() == o.agent_count(), step
+        r = P.compare_states(g.read_state(), o.read_state())  # includes next_waypoint
+        assert r["vel_rel_err"] <= 1e-12 and r["pos_rel_err"] <= 1e-12  # only IEEE +,-,*,/,sqrt involved
+    assert destroyed > 0
+    # plain agents of a route planner are not in its cache: None -> velocity 0 (rmf/mod.rs:211-214) ...
+    hl = R.RouteFollowPlan([(5.0, 5.0), (9.0, 5.0)])
+    g2 = R.Simulation(R.LocationHash2D(32.0, 32.0, 2.0, (0.0, 0.0), capacity=16))
+    ids = g2.add_agents([(1.0, 5.0), (2.0, 9.0)], hl, R.NoLocalPlan(), 1.0)
+    g2.step(R.Duration(1, 0))
+    st = g2.read_state()
+    assert list(st["x"]) == [1.0, 2.0] and list(st["vx"]) == [0.0, 0.0]
+    # ... until set_target enters them
+    g2.route_set_target([ids[0]])
+    g2.step(R.Duration(1, 0))
+    st = g2.read_state()
+    assert list(st["x"]) == [2.0, 2.0] and list(st["vx"]) == [1.0, 0.0] and list(st["next_waypoint"]) == [0, 0]
