@@ -140,15 +140,17 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 6) step_warp_kernel(StepArgs a)
   {
     const uint32_t x0 = __reduce_max_sync(FULL, l0), x1 = __reduce_max_sync(FULL, l1),
                    x2 = __reduce_max_sync(FULL, l2);
+    // Branch-free body: a lane that has run out of candidates re-reads its own slot, which the self filter
+    // rejects; the loads of the unrolled iterations are independent and go out together.
+    const uint32_t iself = active ? i : 0u;  /* lanes without an agent have L = 0 and thr2 = 0 */
 #define RCS_FILTER_SLICE(MX, S, L, M)                                  \
+    _Pragma("unroll 4")                                                \
     for (uint32_t t = 0; t < (MX); ++t) {                              \
-      if (t < (L)) {                                                   \
-        const uint32_t j = (S) + t;                                    \
-        const double dx = xs[j] - me.px;                               \
-        const double dy = ys[j] - me.py;                               \
-        const double d2 = dx * dx + dy * dy;                           \
-        if ((d2 < thr2) && (j != i)) (M) |= 1u << t;                   \
-      }                                                                \
+      const uint32_t j = (t < (L)) ? (S) + t : iself;                  \
+      const double dx = xs[j] - me.px;                                 \
+      const double dy = ys[j] - me.py;                                 \
+      const double d2 = dx * dx + dy * dy;                             \
+      (M) |= ((d2 < thr2) && (j != i)) ? (1u << t) : 0u;               \
     }
     RCS_FILTER_SLICE(x0, s0, l0, m0)
     RCS_FILTER_SLICE(x1, s1, l1, m1)
@@ -188,54 +190,64 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 6) step_warp_kernel(StepArgs a)
         __syncwarp();
       };
       // (word, slice start) queue of this lane; empty words are popped with predicated moves, so the walk over
-      // the three slices stays free of divergent branches
+      // the three slices stays free of divergent branches.  Two neighbours are taken per iteration: their loads
+      // and arithmetic are independent, which hides half of the load and FP64 latency at this occupancy.
       uint32_t bits = m0, base = s0, nb1 = m1, ns1 = s1, nb2 = m2, ns2 = s2, k = 0;
+      const uint32_t iself = active ? i : 0u;
+      auto take = [&](uint32_t& j, uint32_t& t, uint32_t& kk) -> bool {
+        const bool empty = bits == 0u;  // one pop per take: a lane with two empty words in a row idles once
+        bits = empty ? nb1 : bits;
+        base = empty ? ns1 : base;
+        nb1 = empty ? nb2 : nb1;
+        ns1 = empty ? ns2 : ns1;
+        nb2 = empty ? 0u : nb2;
+        k += empty ? 1u : 0u;
+        const bool v = bits != 0u;
+        t = v ? (uint32_t)(__ffs(bits) - 1) : 0u;
+        bits &= bits - 1u;          // 0 stays 0
+        j = v ? base + t : iself;   // always a valid slot: no branch around the loads
+        kk = k;
+        return v;
+      };
+      // the division-free half of time_to_collision for neighbour j; same operations as rcs_math.cuh
+      auto probe = [&](bool v, uint32_t j, uint32_t t, uint32_t kk) -> bool {
+        const uint32_t bit = (v && me.id < ids[j]) ? (1u << t) : 0u;
+        y0 |= (kk == 0u) ? bit : 0u;
+        y1 |= (kk == 1u) ? bit : 0u;
+        y2 |= (kk == 2u) ? bit : 0u;
+        const double dx = xs[j] - me.px;
+        const double dy = ys[j] - me.py;
+        const double rvx = vxs[j] - me.vx;
+        const double rvy = vys[j] - me.vy;
+        const double qa = rvx * rvx + rvy * rvy;
+        const double d2 = dx * dx + dy * dy;
+        const double qb = 2.0 * (rvx * dx + rvy * dy);
+        const double qc = d2 - rr;
+        const double bb = qb * qb;
+        const double disc = bb - (4.0 * qa) * qc;
+        // A finite time needs a > 0, disc >= 0 and -b + sqrt(disc) > 0.  For b >= 0, disc <= b*b gives
+        // sqrt(disc) <= sqrt(fl(b*b)) = b (correctly rounded sqrt of a square is exact and monotone), so the
+        // numerator is <= 0: INF.  disc == b*b is passed on although it cannot be finite either, so that one
+        // compare also covers b*b = inf.  Everything else is decided by the literal routine on the list.
+        return v && (qa > 0.0) && (disc >= 0.0) && ((qb < 0.0) || !(disc < bb));
+      };
       while (__any_sync(FULL, (bits | nb1 | nb2) != 0u)) {
-        bool hit = false;
-        uint32_t j = 0;
-#pragma unroll
-        for (int pop = 0; pop < 1; ++pop) {  // one pop per iteration: a lane with two empty words idles once
-          const bool empty = bits == 0u;
-          bits = empty ? nb1 : bits;
-          base = empty ? ns1 : base;
-          nb1 = empty ? nb2 : nb1;
-          ns1 = empty ? ns2 : ns1;
-          nb2 = empty ? 0u : nb2;
-          k += empty ? 1u : 0u;
-        }
-        if (bits != 0u) {
-          const uint32_t t = __ffs(bits) - 1;
-          bits &= bits - 1u;
-          j = base + t;
-          const uint32_t bit = (me.id < ids[j]) ? (1u << t) : 0u;
-          y0 |= (k == 0u) ? bit : 0u;
-          y1 |= (k == 1u) ? bit : 0u;
-          y2 |= (k == 2u) ? bit : 0u;
-          // the division-free half of time_to_collision; same operations as rcs_math.cuh
-          const double dx = xs[j] - me.px;
-          const double dy = ys[j] - me.py;
-          const double rvx = vxs[j] - me.vx;
-          const double rvy = vys[j] - me.vy;
-          const double qa = rvx * rvx + rvy * rvy;
-          if (qa > 0.0) {
-            const double d2 = dx * dx + dy * dy;
-            const double qb = 2.0 * (rvx * dx + rvy * dy);
-            const double qc = d2 - rr;
-            const double bb = qb * qb;
-            const double disc = bb - (4.0 * qa) * qc;
-            // A finite time needs disc >= 0 and -b + sqrt(disc) > 0.  For b >= 0, disc <= b*b gives
-            // sqrt(disc) <= sqrt(fl(b*b)) = b (correctly rounded sqrt of a square is exact and monotone), so the
-            // numerator is <= 0: INF.  disc == b*b is passed on although it cannot be finite either, so that one
-            // compare also covers b*b = inf.  Everything else is decided by the literal routine on the list.
-            hit = (disc >= 0.0) && ((qb < 0.0) || !(disc < bb));
-          }
-        }
-        if (hit) {  // order inside the list is irrelevant (min): a shared counter hands out the slots
+        uint32_t jA, tA, kA, jB, tB, kB;
+        const bool vA = take(jA, tA, kA);
+        const bool vB = take(jB, tB, kB);
+        const bool hitA = probe(vA, jA, tA, kA);
+        const bool hitB = probe(vB, jB, tB, kB);
+        if (hitA) {  // order inside the list is irrelevant (min): a shared counter hands out the slots
           const uint32_t pos = atomicAdd(&w.hcnt, 1u);
-          w.lj[pos] = j;
+          w.lj[pos] = jA;
           w.lo[pos] = (uint8_t)lane;
         }
-        if ((++it & 3u) == 0u) {  // at most 4 x 32 new entries since the last look at the counter
+        if (hitB) {
+          const uint32_t pos = atomicAdd(&w.hcnt, 1u);
+          w.lj[pos] = jB;
+          w.lo[pos] = (uint8_t)lane;
+        }
+        if ((++it & 1u) == 0u) {  // at most 2 x 64 new entries since the last look at the counter
           __syncwarp();
           if (*(volatile uint32_t*)&w.hcnt > 2 * SW_CAP - 128) flush_hits();
         }
