@@ -210,7 +210,7 @@ static int sort_into_srt(rcs_sim* s, uint32_t n_ub) {
                                                      4096, s->d_status);
     gather_sorted_kernel<<<blocks_for(n_ub, 256), 256, 0, s->stream>>>(
         n_ub, s->perm, s->cur, s->srt, s->cellid, s->strip.enabled ? s->srt_cell : nullptr, s->cell_start + len,
-        s->d_status);
+        s->grid, s->cell_start, s->d_groups, s->d_groups ? s->slices : nullptr, s->d_status);
     s->launches += 4;
   }
   CU_TRY(s, cudaGetLastError());
@@ -219,7 +219,9 @@ static int sort_into_srt(rcs_sim* s, uint32_t n_ub) {
 
 // (Re)build the canonical (cell, id) sorted copy `srt` of `cur` and cell_start (no step in flight).
 static int build_index(rcs_sim* s) {
-  int rc = upload_counts(s);
+  int rc = upload_groups(s);  // gather_sorted_kernel reads the group table
+  if (rc) return rc;
+  rc = upload_counts(s);
   if (rc) return rc;
   CU_TRY(s, cudaMemsetAsync(s->cell_count, 0, (s->grid.len + 1) * sizeof(uint32_t), s->stream));
   rc = bin_agents(s, s->n, nullptr);

@@ -297,26 +297,59 @@ __global__ void sort_big_cells_kernel(const uint32_t* __restrict__ cell_start, c
   }
 }
 
-// Physical reorder into canonical order: sorted[k] = cur[perm[k]].
+// Physical reorder into canonical order: sorted[k] = cur[perm[k]].  This kernel is HBM-bound with idle issue
+// slots, so it also prepares the radius query of every Zanlungo agent for the hot kernel: the (at most three)
+// candidate slices of the sorted arrays, one per stencil column (get_bounds + signed_idx_to_data_idx,
+// location_hash_2d.rs:74-122), as {start0, start1, start2, len0 | len1 << 8 | len2 << 16 | ok << 24}.
+// ok = 0: the stencil is wider than three columns (the agent takes the sequential routine); lengths saturate
+// at 255.
 __global__ void gather_sorted_kernel(uint32_t n, const uint32_t* __restrict__ perm, AgentArrays cur,
                                      AgentArrays srt, const uint32_t* __restrict__ cellid,
                                      uint32_t* __restrict__ srt_cell, const uint32_t* __restrict__ n_sorted,
+                                     GridDev g, const uint32_t* __restrict__ cell_start,
+                                     const GroupDev* __restrict__ groups, uint4* __restrict__ slices,
                                      const DevStatus* status) {
   if (status->failed) return;
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n || k >= *n_sorted) return;
   uint32_t i = perm[k];
   if (srt_cell) srt_cell[k] = cellid[i];
-  srt.x[k] = cur.x[i];
-  srt.y[k] = cur.y[i];
+  const double px = cur.x[i], py = cur.y[i];
+  const uint32_t grp = cur.grp[i];
+  srt.x[k] = px;
+  srt.y[k] = py;
   srt.vx[k] = cur.vx[i];
   srt.vy[k] = cur.vy[i];
   srt.id[k] = cur.id[i];
-  srt.grp[k] = cur.grp[i];
+  srt.grp[k] = grp;
   srt.wp[k] = cur.wp[i];
   if (cur.pvx) {
     srt.pvx[k] = cur.pvx[i];
     srt.pvy[k] = cur.pvy[i];
+  }
+  if (slices) {
+    uint4 sl = make_uint4(0u, 0u, 0u, 0u);
+    const GroupDev& gr = groups[grp];
+    if (gr.lp_kind == LP_ZANLUNGO) {
+      int64_t left, right, bottom, top;
+      get_bounds(g, gr.eyesight, px, py, left, right, bottom, top);
+      if (left < 0) left = 0;
+      if (right > g.x_max) right = g.x_max;
+      if (right - left <= 2) {
+        uint32_t st[3] = {0, 0, 0}, ln[3] = {0, 0, 0};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          uint64_t c_lo, c_hi;
+          if (left + c <= right && column_cell_range(g, left + c, bottom, top, c_lo, c_hi)) {
+            st[c] = cell_start[c_lo];
+            const uint32_t l = cell_start[c_hi + 1] - st[c];
+            ln[c] = l > 255u ? 255u : l;
+          }
+        }
+        sl = make_uint4(st[0], st[1], st[2], ln[0] | (ln[1] << 8) | (ln[2] << 16) | (1u << 24));
+      }
+    }
+    slices[k] = sl;
   }
 }
 
@@ -353,6 +386,7 @@ struct StepArgs {
   unsigned long long* ev_destroyed;  // (id, step) pairs of agents removed at sinks
   uint32_t ev_cap;
   uint32_t* slow_list;             // warp kernel: agents left to the sequential kernel
+  const uint4* slices;             // candidate slices prepared by gather_sorted_kernel (sorted path only)
   const double* routes;            // HL_ROUTE polylines, interleaved x,y
   double route_thr2;               // smallest double T with sqrt(T) >= 1e-1 (rmf/mod.rs:202)
 };

@@ -66,7 +66,6 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 6) step_warp_kernel(StepArgs a)
   const double* __restrict__ vxs = a.in.vx;
   const double* __restrict__ vys = a.in.vy;
   const uint64_t* __restrict__ ids = a.in.id;
-  const uint32_t* __restrict__ cell_start = a.cell_start;
 
   Self me;
   me.px = me.py = me.vx = me.vy = me.pfx = me.pfy = 0.0;
@@ -102,27 +101,14 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 6) step_warp_kernel(StepArgs a)
     thr2 = g.thr2;
     rr = g.rr;
     if (zan) {
-      int64_t left, right, bottom, top;
-      get_bounds(a.grid, g.eyesight, me.px, me.py, left, right, bottom, top);
-      if (left < 0) left = 0;
-      if (right > a.grid.x_max) right = a.grid.x_max;
-      // ids >= 2^53 round when they become priorities (zanlungo.rs:94) and groups whose weight-0 pairs cannot be
-      // proven zero need the literal routine for every pair: both are left to the sequential kernel
-      fast = (right - left) <= 2 && g.w0_fast && (me.id >> 53) == 0ull;
-      if (fast) {
-        uint32_t s[3] = {0, 0, 0}, l[3] = {0, 0, 0};
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          uint64_t c_lo, c_hi;
-          if (left + k <= right && column_cell_range(a.grid, left + k, bottom, top, c_lo, c_hi)) {
-            s[k] = cell_start[c_lo];
-            l[k] = cell_start[c_hi + 1] - s[k];
-          }
-        }
-        s0 = s[0]; s1 = s[1]; s2 = s[2];
-        l0 = l[0]; l1 = l[1]; l2 = l[2];
-        fast = l0 <= SW_SLICE_MAX && l1 <= SW_SLICE_MAX && l2 <= SW_SLICE_MAX;
-      }
+      // candidate slices of the radius query, prepared by gather_sorted_kernel.  ids >= 2^53 round when they
+      // become priorities (zanlungo.rs:94) and groups whose weight-0 pairs cannot be proven zero need the literal
+      // routine for every pair: both are left to the sequential kernel, like wide or crowded stencils
+      const uint4 sl = a.slices[i];
+      s0 = sl.x; s1 = sl.y; s2 = sl.z;
+      l0 = sl.w & 0xffu; l1 = (sl.w >> 8) & 0xffu; l2 = (sl.w >> 16) & 0xffu;
+      fast = (sl.w >> 24) != 0u && g.w0_fast && (me.id >> 53) == 0ull && l0 <= SW_SLICE_MAX &&
+             l1 <= SW_SLICE_MAX && l2 <= SW_SLICE_MAX;
       if (!fast) {
         // wide stencil or crowded cells: this agent is finished by step_slow_kernel (sequential routine)
         l0 = l1 = l2 = 0;
