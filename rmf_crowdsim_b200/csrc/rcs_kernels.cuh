@@ -547,8 +547,8 @@ __device__ __forceinline__ void high_level_velocity(const StepArgs& a, uint32_t 
 // Explicit Euler + commit outputs + error accounting (lib.rs:295-302), then the waypoint / sink test on
 // the OLD position (lib.rs:305-336) and, for strips, the ownership decision by the NEW position.
 __device__ __forceinline__ void integrate_and_store(const StepArgs& a, uint32_t i, const Self& me, const GroupDev& g,
-                                                    uint32_t grp, uint32_t role, double velx, double vely, double t_i,
-                                                    double fx, double fy, uint32_t nbc) {
+                                                    uint32_t grp, uint32_t wp_in, uint32_t role, double velx,
+                                                    double vely, double t_i, double fx, double fy, uint32_t nbc) {
   const double nx = me.px + velx * a.dt;
   const double ny = me.py + vely * a.dt;
   a.ox[i] = nx;
@@ -576,7 +576,6 @@ __device__ __forceinline__ void integrate_and_store(const StepArgs& a, uint32_t 
   if (own && !(isfinite(nx) && isfinite(ny) && isfinite(velx) && isfinite(vely)))
     atomicAdd(&a.status->nonfinite_count, 1u);
   if (!a.oid) return;  // streaming path: x,y,vx,vy only
-  const uint32_t wp_in = a.in.wp[i];
   uint32_t wp = wp_in & WP_MASK;
   uint32_t rwp = g.hl_kind == HL_ROUTE ? me.rwp : (wp_in >> WP_ROUTE_SHIFT);
   bool keep = true;
@@ -678,7 +677,7 @@ __device__ __forceinline__ void step_one_agent(const StepArgs& a, uint32_t i, ui
     velx = velx + fx * g.inv_mass;
     vely = vely + fy * g.inv_mass;
   }
-  integrate_and_store(a, i, me, g, a.in.grp[i], role, velx, vely, t_i, fx, fy, nb);
+  integrate_and_store(a, i, me, g, a.in.grp[i], a.oid ? a.in.wp[i] : 0u, role, velx, vely, t_i, fx, fy, nb);
   if (role == ROLE_OWN) {  // statistics are per owned agent so that they add up over ranks
     cand += c;
     nbc += nb;

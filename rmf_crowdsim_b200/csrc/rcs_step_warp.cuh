@@ -52,14 +52,11 @@ struct WarpShared {
 };
 
 __global__ void __launch_bounds__(32 * SW_WARPS, 6) step_warp_kernel(StepArgs a) {
-  if (a.status->failed) return;
   __shared__ WarpShared sh[SW_WARPS];
   WarpShared& w = sh[threadIdx.x >> 5];
   const unsigned lane = threadIdx.x & 31u;
   const unsigned FULL = 0xffffffffu;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t n_live = *a.n_sorted;
-  bool active = (i < a.n) && (i < n_live);
 
   const double* __restrict__ xs = a.in.x;
   const double* __restrict__ ys = a.in.y;
@@ -67,12 +64,31 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 6) step_warp_kernel(StepArgs a)
   const double* __restrict__ vys = a.in.vy;
   const uint64_t* __restrict__ ids = a.in.id;
 
+  // This warp's own rows go out first, before the status words are even looked at: every array holds at least
+  // a.n entries, so the loads are safe for i < a.n and their (DRAM) latency overlaps the dependent checks below.
   Self me;
   me.px = me.py = me.vx = me.vy = me.pfx = me.pfy = 0.0;
   me.id = 0;
   me.rwp = 0u;
+  uint32_t grp = 0, wp_in = 0;
+  uint4 sl = make_uint4(0u, 0u, 0u, 0u);
+  const bool inb = i < a.n;
+  if (inb) {
+    me.px = xs[i];
+    me.py = ys[i];
+    me.vx = vxs[i];
+    me.vy = vys[i];
+    me.id = ids[i];
+    grp = a.in.grp[i];
+    wp_in = a.in.wp[i];
+    sl = a.slices[i];
+  }
+  if (a.status->failed) return;
+  const uint32_t n_live = *a.n_sorted;
+  bool active = inb && (i < n_live);
+
   double velx = 0.0, vely = 0.0, thr2 = 0.0, rr = 0.0;
-  uint32_t grp = 0, role = ROLE_PASSIVE;
+  uint32_t role = ROLE_PASSIVE;
   bool zan = false;
   uint32_t s0 = 0, s1 = 0, s2 = 0, l0 = 0, l1 = 0, l2 = 0;  // candidate slices of this lane (cooperative path)
   bool fast = false;
@@ -89,13 +105,7 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 6) step_warp_kernel(StepArgs a)
     a.keep[i] = 0u;
   }
   if (active) {
-    grp = a.in.grp[i];
     const GroupDev& g = a.groups[grp];
-    me.px = xs[i];
-    me.py = ys[i];
-    me.vx = vxs[i];
-    me.vy = vys[i];
-    me.id = ids[i];
     high_level_velocity(a, i, g, me, velx, vely);
     zan = g.lp_kind == LP_ZANLUNGO;
     thr2 = g.thr2;
@@ -104,7 +114,6 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 6) step_warp_kernel(StepArgs a)
       // candidate slices of the radius query, prepared by gather_sorted_kernel.  ids >= 2^53 round when they
       // become priorities (zanlungo.rs:94) and groups whose weight-0 pairs cannot be proven zero need the literal
       // routine for every pair: both are left to the sequential kernel, like wide or crowded stencils
-      const uint4 sl = a.slices[i];
       s0 = sl.x; s1 = sl.y; s2 = sl.z;
       l0 = sl.w & 0xffu; l1 = (sl.w >> 8) & 0xffu; l2 = (sl.w >> 16) & 0xffu;
       fast = (sl.w >> 24) != 0u && g.w0_fast && (me.id >> 53) == 0ull && l0 <= SW_SLICE_MAX &&
@@ -304,14 +313,22 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 6) step_warp_kernel(StepArgs a)
         const uint32_t lane_end = (okm == FULL) ? 32u : (uint32_t)(__ffs(~okm) - 1);  // > lane_begin: cA, cB <= 96
         const bool part = lane >= lane_begin && lane < lane_end;
         if (part) {
-          uint32_t p = offA;
-          for (uint32_t bits = a0; bits; bits &= bits - 1u) { w.lj[p] = s0 + __ffs(bits) - 1; w.lo[p] = (uint8_t)lane; ++p; }
-          for (uint32_t bits = a1; bits; bits &= bits - 1u) { w.lj[p] = s1 + __ffs(bits) - 1; w.lo[p] = (uint8_t)lane; ++p; }
-          for (uint32_t bits = a2; bits; bits &= bits - 1u) { w.lj[p] = s2 + __ffs(bits) - 1; w.lo[p] = (uint8_t)lane; ++p; }
-          p = SW_CAP + offB;
-          for (uint32_t bits = z0; bits; bits &= bits - 1u) { w.lj[p] = s0 + __ffs(bits) - 1; w.lo[p] = (uint8_t)lane; ++p; }
-          for (uint32_t bits = z1; bits; bits &= bits - 1u) { w.lj[p] = s1 + __ffs(bits) - 1; w.lo[p] = (uint8_t)lane; ++p; }
-          for (uint32_t bits = z2; bits; bits &= bits - 1u) { w.lj[p] = s2 + __ffs(bits) - 1; w.lo[p] = (uint8_t)lane; ++p; }
+          // one walk per slice feeds both lists: yield pairs to A, weight-0 pairs to B
+          uint32_t pA = offA, pB = SW_CAP + offB;
+#define RCS_EMIT_SLICE(A, Z, S)                                          \
+          for (uint32_t bits = (A) | (Z); bits; bits &= bits - 1u) {     \
+            const uint32_t t = __ffs(bits) - 1;                          \
+            const bool yv = (((A) >> t) & 1u) != 0u;                     \
+            const uint32_t pos = yv ? pA : pB;                           \
+            w.lj[pos] = (S) + t;                                         \
+            w.lo[pos] = (uint8_t)lane;                                   \
+            pA += yv ? 1u : 0u;                                          \
+            pB += yv ? 0u : 1u;                                          \
+          }
+          RCS_EMIT_SLICE(a0, z0, s0)
+          RCS_EMIT_SLICE(a1, z1, s1)
+          RCS_EMIT_SLICE(a2, z2, s2)
+#undef RCS_EMIT_SLICE
         }
         const uint32_t tot = __shfl_sync(FULL, inc, lane_end - 1) - base;
         const uint32_t nA = tot & 0xffffu, nB = tot >> 16;
@@ -360,7 +377,7 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 6) step_warp_kernel(StepArgs a)
       velx = velx + fx * g.inv_mass;
       vely = vely + fy * g.inv_mass;
     }
-    integrate_and_store(a, i, me, g, grp, role, velx, vely, t_i, fx, fy, nbc);
+    integrate_and_store(a, i, me, g, grp, wp_in, role, velx, vely, t_i, fx, fy, nbc);
   }
   const bool own = active && role == ROLE_OWN;
   warp_stats(a, own ? cand : 0u, own ? nbc : 0u, (own && zan && t_i != RCS_INF) ? 1u : 0u);
