@@ -565,8 +565,8 @@ __device__ __forceinline__ void integrate_and_store(const StepArgs& a, uint32_t 
     a.tr_own[i] = own ? 1u : 0u;
   }
   // add_or_update(new_pos) error path, lib.rs:299-302
-  const uint64_t x_idx = f64_as_usize((nx - a.grid.offx) / a.grid.res);
-  const uint64_t y_idx = f64_as_usize((ny - a.grid.offy) / a.grid.res);
+  const uint64_t x_idx = f64_as_usize(div_floor(nx - a.grid.offx, a.grid));
+  const uint64_t y_idx = f64_as_usize(div_floor(ny - a.grid.offy, a.grid));
   const uint64_t idx = x_idx * a.grid.nx + y_idx;
   const bool inb = idx < a.grid.len;
   if (!inb && own) {
@@ -750,8 +750,8 @@ __global__ void query_radius_kernel(GridDev g, const uint32_t* __restrict__ cell
 // ---------------------------------------------------------------------------------------------
 template <class F>
 __device__ __forceinline__ uint64_t knn_walk(const GridDev& g, double px, double py, uint64_t n, F&& f) {
-  const int64_t x_idx = f64_floor_as_i64((px - g.offx) / g.res);  // location_to_xy_signed_idx, :68-72
-  const int64_t y_idx = f64_floor_as_i64((py - g.offy) / g.res);
+  const int64_t x_idx = f64_floor_as_i64(div_floor(px - g.offx, g));  // location_to_xy_signed_idx, :68-72
+  const int64_t y_idx = f64_floor_as_i64(div_floor(py - g.offy, g));
   uint64_t have = 0;
   bool all_oob = false;
   auto visit = [&](int64_t cx, int64_t cy, uint64_t& oob) {

@@ -21,7 +21,21 @@ struct GridDev {
   uint64_t nx;    // (width / resolution) as usize -- the stride used by BOTH index formulas (:59, :79)
   uint64_t len;   // data.len() = nx * ny
   int64_t x_max;  // largest x_idx that can still give idx < len for some y >= 0; -1 if len == 0
+  double inv_res; // 1 / res, only ever used to PREDICT a quotient (see div_floor)
 };
+
+// floor(fl(num / res)) -- the floor of the correctly rounded IEEE quotient the reference computes
+// (location_hash_2d.rs:56-57, 69-70) -- without a division in the common case.  q1 = fl(num * fl(1/res)) is within
+// 2 ulp of the true quotient and the IEEE quotient within 0.5 ulp, so when q1 is further than 8 ulp from every
+// integer all three have the same floor.  Otherwise (q1 next to an integer, huge, NaN) the true division decides.
+__device__ __forceinline__ double div_floor(double num, const GridDev& g) {
+  const double q1 = num * g.inv_res;
+  const double f = floor(q1);
+  const double d = q1 - f;                              // [0, 1): exact (Sterbenz) or q1 is huge and d == 0
+  const double tol = fabs(q1) * 1.8e-15 + 1e-300;       // 8 ulp
+  if (d > tol && (1.0 - d) > tol) return f;
+  return floor(num / g.res);
+}
 
 // One add_agents group = (high-level planner, local planner, eyesight) (lib.rs:119-125).
 struct GroupDev {
@@ -59,8 +73,9 @@ __device__ __forceinline__ int64_t f64_floor_as_i64(double v) {
 // LocationHash2D::location_to_index (location_hash_2d.rs:54-66): insert cell.  Returns false when
 // the reference returns Err("Index out of bounds").
 __device__ __forceinline__ bool location_to_index(const GridDev& g, double px, double py, uint64_t& idx) {
-  uint64_t x_idx = f64_as_usize((px - g.offx) / g.res);
-  uint64_t y_idx = f64_as_usize((py - g.offy) / g.res);
+  // trunc toward zero == floor for the positive quotients; everything <= 0 (and NaN) saturates to 0 either way
+  uint64_t x_idx = f64_as_usize(div_floor(px - g.offx, g));
+  uint64_t y_idx = f64_as_usize(div_floor(py - g.offy, g));
   idx = x_idx * g.nx + y_idx;  // wrapping, as release-mode Rust
   return idx < g.len;
 }
@@ -68,10 +83,10 @@ __device__ __forceinline__ bool location_to_index(const GridDev& g, double px, d
 // LocationHash2D::get_bounds (location_hash_2d.rs:103-122): query cell bounds (floor, not trunc).
 __device__ __forceinline__ void get_bounds(const GridDev& g, double radius, double px, double py, int64_t& left,
                                            int64_t& right, int64_t& bottom, int64_t& top) {
-  right = f64_floor_as_i64(((px + radius) - g.offx) / g.res);
-  left = f64_floor_as_i64(((px - radius) - g.offx) / g.res);
-  top = f64_floor_as_i64(((py + radius) - g.offy) / g.res);
-  bottom = f64_floor_as_i64(((py - radius) - g.offy) / g.res);
+  right = f64_floor_as_i64(div_floor((px + radius) - g.offx, g));
+  left = f64_floor_as_i64(div_floor((px - radius) - g.offx, g));
+  top = f64_floor_as_i64(div_floor((py + radius) - g.offy, g));
+  bottom = f64_floor_as_i64(div_floor((py - radius) - g.offy, g));
 }
 
 // For column x of the scan `for x in left..=right { for y in bottom..=top }` (location_hash_2d.rs:245-246)
