@@ -398,11 +398,17 @@ def main():
     ap.add_argument("--variant", default="shuffled", choices=["shuffled", "lane"])
     ap.add_argument("--no-local-plan", action="store_true")
     ap.add_argument("--kernel", type=int, default=0, help="RCS_OPT_STEP_KERNEL: 0 default, 1 thread/agent, 2 warp")
+    ap.add_argument("--c5-zanlungo", action="store_true", help="--workload c5 with the Zanlungo planner")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.workload == "c5":
+        from rmf_crowdsim_b200 import stream_bench
+
+        stream_bench.run(args)
         return
     if args.gpus == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
         run_gpu_single(args)

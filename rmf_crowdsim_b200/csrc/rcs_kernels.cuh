@@ -275,25 +275,53 @@ __global__ void sort_cells_by_id_kernel(uint64_t len, const uint32_t* __restrict
   for (uint32_t k = 0; k < m; ++k) perm[s + k] = p[k];
 }
 
-// One block per oversized cell: rank = number of smaller ids (ids are unique), O(m^2 / threads).
-__global__ void sort_big_cells_kernel(const uint32_t* __restrict__ cell_start, const uint64_t* __restrict__ id,
-                                      uint32_t* __restrict__ perm, uint32_t* __restrict__ scratch,
-                                      const uint32_t* __restrict__ big_list, uint32_t big_cap,
-                                      const DevStatus* status) {
-  if (status->failed) return;
-  uint32_t nbig = status->big_cells < big_cap ? status->big_cells : big_cap;
-  for (uint32_t b = blockIdx.x; b < nbig; b += gridDim.x) {
-    uint32_t c = big_list[b];
-    uint32_t s = cell_start[c], e = cell_start[c + 1];
-    for (uint32_t k = s + threadIdx.x; k < e; k += blockDim.x) {
-      uint64_t kk = id[perm[k]];
-      uint32_t rank = 0;
+// One block per oversized cell: rank = number of smaller ids (ids are unique), O(m^2 / threads), keys staged in
+// shared memory when the cell holds at most BIG_SMEM_KEYS agents.  The cells come from big_list; if more cells
+// were oversized than the list holds (big_cells > big_cap) every block sweeps a share of ALL cells instead.
+constexpr uint32_t BIG_SMEM_KEYS = 4096;
+
+__device__ __forceinline__ void sort_one_big_cell(uint32_t s, uint32_t e, const uint64_t* __restrict__ id,
+                                                  uint32_t* __restrict__ perm, uint32_t* __restrict__ scratch,
+                                                  unsigned long long* skeys) {
+  const uint32_t m = e - s;
+  const bool in_smem = m <= BIG_SMEM_KEYS;
+  if (in_smem)
+    for (uint32_t k = threadIdx.x; k < m; k += blockDim.x) skeys[k] = id[perm[s + k]];
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < m; k += blockDim.x) {
+    const uint64_t kk = in_smem ? skeys[k] : id[perm[s + k]];
+    uint32_t rank = 0;
+    if (in_smem) {
+      for (uint32_t j = 0; j < m; ++j) rank += (skeys[j] < kk) ? 1u : 0u;
+    } else {
       for (uint32_t j = s; j < e; ++j) rank += (id[perm[j]] < kk) ? 1u : 0u;
-      scratch[s + rank] = perm[k];
     }
-    __syncthreads();
-    for (uint32_t k = s + threadIdx.x; k < e; k += blockDim.x) perm[k] = scratch[k];
-    __syncthreads();
+    scratch[s + rank] = perm[s + k];
+  }
+  __syncthreads();
+  for (uint32_t k = s + threadIdx.x; k < e; k += blockDim.x) perm[k] = scratch[k];
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) sort_big_cells_kernel(uint64_t len, const uint32_t* __restrict__ cell_start,
+                                                              const uint64_t* __restrict__ id,
+                                                              uint32_t* __restrict__ perm,
+                                                              uint32_t* __restrict__ scratch,
+                                                              const uint32_t* __restrict__ big_list, uint32_t big_cap,
+                                                              const DevStatus* status) {
+  __shared__ unsigned long long skeys[BIG_SMEM_KEYS];
+  if (status->failed) return;
+  const uint32_t nbig = status->big_cells;
+  if (nbig <= big_cap) {
+    for (uint32_t b = blockIdx.x; b < nbig; b += gridDim.x) {
+      const uint32_t c = big_list[b];
+      sort_one_big_cell(cell_start[c], cell_start[c + 1], id, perm, scratch, skeys);
+    }
+  } else {
+    for (uint64_t c = blockIdx.x; c < len; c += gridDim.x) {  // block-uniform: every thread sees the same bounds
+      const uint32_t cs = cell_start[c], ce = cell_start[c + 1];
+      if (ce - cs > SORT_LOCAL_MAX) sort_one_big_cell(cs, ce, id, perm, scratch, skeys);
+    }
   }
 }
 

@@ -281,3 +281,24 @@ def test_warp_cooperative_kernel_is_bit_identical_to_thread_per_agent(variant):
             assert np.array_equal(sa[k].view(np.uint64), sb[k].view(np.uint64)), k
     assert sims[0].stats().neighbour_total == sims[1].stats().neighbour_total
     assert sims[0].stats().candidate_total == sims[1].stats().candidate_total
+
+
+def test_more_oversized_cells_than_the_big_cell_list_holds():
+    """4900 cells with 40 agents each (> 32 per cell, > 4096 such cells): the block sorter sweeps all cells and
+    storage order is still canonical (cell, then ascending id)."""
+    rng = np.random.default_rng(3)
+    side, per = 70, 40
+    cell = 4.0
+    cx, cy = np.meshgrid(np.arange(side), np.arange(side), indexing="ij")
+    base = np.stack([cx.reshape(-1), cy.reshape(-1)], axis=1).astype(np.float64) * cell
+    xy = (base[:, None, :] + rng.uniform(0.05, cell - 0.05, size=(side * side, per, 2))).reshape(-1, 2)
+    xy = xy[rng.permutation(len(xy))]
+    idx = R.LocationHash2D(side * cell, side * cell, cell, (0.0, 0.0), capacity=len(xy))
+    sim = R.Simulation(idx)
+    sim.add_agents(xy, R.ConstantVelocityPlan((0.0, 0.0)), R.Zanlungo(0.05, 1.0, 0.0, 0.5, 1.0, 0.01), 0.05)
+    sim.step(R.Duration(0, 1_000_000))
+    st = sim.read_state(order=R._native.RCS_ORDER_STORAGE)
+    cells = idx.cell_of(np.stack([st["x"], st["y"]], axis=1))
+    key = cells.astype(np.uint64) * np.uint64(1 << 32) + st["id"]
+    assert np.all(key[1:] > key[:-1])
+    assert len(st["id"]) == len(xy) and sim.stats().oob_count == 0
