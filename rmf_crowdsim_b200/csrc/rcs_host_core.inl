@@ -138,6 +138,7 @@ static uint32_t find_or_add_group(rcs_sim* s, uint32_t hl, uint32_t lp, double e
     g.inv_mass = 1.0 / L.agent_mass;
     g.rr = L.agent_radius * L.agent_radius;
     g.two_r = L.agent_radius * 2.0;
+    g.inv_fd = 1.0 / L.force_distance;
     // weight-0 pairs can be skipped only if 0*agent_scale == 0 and exp(-(dist - 2r)/D) cannot overflow
     bool ok = std::isfinite(L.agent_scale) && L.force_distance > 0.0 && std::isfinite(g.two_r) &&
               (g.two_r / L.force_distance) < 700.0;
