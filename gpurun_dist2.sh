@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+bash gpurun_dist.sh 2
