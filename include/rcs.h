@@ -138,6 +138,13 @@ int rcs_set_preferred_velocity(rcs_sim* sim, uint64_t n, const uint64_t* ids, co
 int rcs_read_agents(rcs_sim* sim, uint32_t order, uint64_t cap, uint64_t* ids, double* x, double* y, double* vx,
                     double* vy, uint32_t* next_waypoint, uint64_t* out_n);
 int rcs_agent_count(rcs_sim* sim, uint64_t* out_n);
+/* The same view without stalling the step stream: the arrays are gathered on the device, copied to the (pinned)
+ * host buffers on a second stream, and the call returns at once, so that the next rcs_set_preferred_velocity /
+ * rcs_step_async overlap with the copies.  The buffers are valid after rcs_read_wait; a second async read waits
+ * (on the device) for the first one's copies.  Use two sets of host buffers to double-buffer. */
+int rcs_read_agents_async(rcs_sim* sim, uint32_t order, uint64_t cap, uint64_t* ids, double* x, double* y, double* vx,
+                          double* vy, uint64_t* out_n);
+int rcs_read_wait(rcs_sim* sim);
 
 /* ---- the hot path ---------------------------------------------------------------------------- */
 

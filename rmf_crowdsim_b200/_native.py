@@ -101,6 +101,8 @@ SIGNATURES = {
         [C.c_void_p, C.c_uint32, C.c_uint64, c_u64p, c_f64p, c_f64p, c_f64p, c_f64p, c_u32p, c_u64p],
     ),
     "rcs_agent_count": (C.c_int, [C.c_void_p, c_u64p]),
+    "rcs_read_agents_async": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, c_u64p, c_f64p, c_f64p, c_f64p, c_f64p, c_u64p]),
+    "rcs_read_wait": (C.c_int, [C.c_void_p]),
     "rcs_step": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32]),
     "rcs_step_async": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32]),
     "rcs_sync": (C.c_int, [C.c_void_p]),

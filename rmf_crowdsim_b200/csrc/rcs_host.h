@@ -146,6 +146,12 @@ struct rcs_sim {
   // staging
   void* stage = nullptr;
   uint64_t stage_bytes = 0;
+  // asynchronous read-back (rcs_read_agents_async): gathers on the main stream, copies on a second one
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_gathered = nullptr, ev_read_done = nullptr;
+  void* stage2 = nullptr;
+  uint64_t stage2_bytes = 0;
+  bool read_inflight = false;
   void* flush_buf = nullptr;
   uint64_t flush_bytes = 0;
   unsigned int* d_bad = nullptr;

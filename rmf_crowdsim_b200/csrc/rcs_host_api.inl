@@ -126,6 +126,13 @@ void rcs_sim_destroy(rcs_sim* s) {
     cudaEventDestroy(pr.second);
   }
   for (auto e : s->kevent_pool) cudaEventDestroy(e);
+  if (s->copy_stream) {
+    cudaStreamSynchronize(s->copy_stream);
+    cudaStreamDestroy(s->copy_stream);
+    cudaEventDestroy(s->ev_gathered);
+    cudaEventDestroy(s->ev_read_done);
+  }
+  cudaFree(s->stage2);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
@@ -523,6 +530,81 @@ int rcs_read_agents(rcs_sim* s, uint32_t order, uint64_t cap, uint64_t* ids, dou
   CU_TRY(s, cudaStreamSynchronize(s->stream));
   if (next_waypoint && s->any_route)  // the high half of the word is the route follower's cache entry
     for (uint32_t k = 0; k < n; ++k) next_waypoint[k] &= WP_MASK;
+  return RCS_OK;
+}
+
+// Read-back that does not stall the step stream: the requested arrays are gathered into a private staging
+// buffer on the step stream (device-speed), the device-to-host copies run on a second stream, and the call
+// returns at once.  The next rcs_set_preferred_velocity / rcs_step_async therefore overlap with the copies
+// (PCIe is full duplex).  The host buffers are valid after rcs_read_wait.
+int rcs_read_agents_async(rcs_sim* s, uint32_t order, uint64_t cap, uint64_t* ids, double* x, double* y, double* vx,
+                          double* vy, uint64_t* out_n) {
+  if (!s) return RCS_ERR_ARG;
+  CU_TRY(s, cudaSetDevice(s->device));
+  int rc = RCS_OK;
+  if (churn(s)) {  // the agent count lives on the device while steps with churn are in flight
+    rc = do_sync(s);
+    if (rc) return rc;
+  }
+  const uint32_t n = s->n;
+  if (out_n) *out_n = n;
+  if (n == 0) return RCS_OK;
+  if (cap < n) {
+    s->err = "output capacity too small";
+    return RCS_ERR_CAPACITY;
+  }
+  if (!s->copy_stream) {
+    CU_TRY(s, cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    CU_TRY(s, cudaEventCreateWithFlags(&s->ev_gathered, cudaEventDisableTiming));
+    CU_TRY(s, cudaEventCreateWithFlags(&s->ev_read_done, cudaEventDisableTiming));
+  }
+  const uint64_t need = (uint64_t)n * 40 + 256;
+  if (need > s->stage2_bytes) {
+    CU_TRY(s, cudaStreamSynchronize(s->copy_stream));
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    cudaFree(s->stage2);
+    s->stage2 = nullptr;
+    s->stage2_bytes = 0;
+    CU_TRY(s, cudaMalloc(&s->stage2, need + need / 4));
+    s->stage2_bytes = need + need / 4;
+  }
+  const uint32_t* ord = nullptr;
+  if (order == RCS_ORDER_ID) {
+    rc = build_slot_table(s);
+    if (rc) return rc;
+    ord = s->order_by_id;
+  }
+  // the previous read's copies must have drained the staging buffer before it is overwritten (device-side wait)
+  if (s->read_inflight) CU_TRY(s, cudaStreamWaitEvent(s->stream, s->ev_read_done, 0));
+  struct Item { const void* src; void* dst; };
+  const Item items[5] = {{s->cur.id, ids}, {s->cur.x, x}, {s->cur.y, y}, {s->cur.vx, vx}, {s->cur.vy, vy}};
+  char* base = static_cast<char*>(s->stage2);
+  for (int k = 0; k < 5; ++k) {
+    if (!items[k].dst) continue;
+    gather_kernel<unsigned long long><<<blocks_for(n, 256), 256, 0, s->stream>>>(
+        n, ord, static_cast<const unsigned long long*>(items[k].src),
+        reinterpret_cast<unsigned long long*>(base + (uint64_t)k * n * 8));  // 8-byte elements, bit copies
+    s->launches += 1;
+  }
+  CU_TRY(s, cudaGetLastError());
+  CU_TRY(s, cudaEventRecord(s->ev_gathered, s->stream));
+  CU_TRY(s, cudaStreamWaitEvent(s->copy_stream, s->ev_gathered, 0));
+  for (int k = 0; k < 5; ++k)
+    if (items[k].dst)
+      CU_TRY(s, cudaMemcpyAsync(items[k].dst, base + (uint64_t)k * n * 8, (uint64_t)n * 8, cudaMemcpyDeviceToHost,
+                                s->copy_stream));
+  CU_TRY(s, cudaEventRecord(s->ev_read_done, s->copy_stream));
+  s->read_inflight = true;
+  return RCS_OK;
+}
+
+int rcs_read_wait(rcs_sim* s) {
+  if (!s) return RCS_ERR_ARG;
+  CU_TRY(s, cudaSetDevice(s->device));
+  if (s->read_inflight) {
+    CU_TRY(s, cudaEventSynchronize(s->ev_read_done));
+    s->read_inflight = false;
+  }
   return RCS_OK;
 }
 

@@ -209,17 +209,20 @@ def run_e2e(sim, scene, steps: int, warmup: int, dist, torch) -> dict:
     out_n = C.c_uint64()
 
     def one():
+        # the download of this step's results runs on a second stream and overlaps the next step's upload + compute
         N.check(h, lib.rcs_set_preferred_velocity(h, n, None, pref.ctypes.data_as(N.c_f64p)))
         N.check(h, lib.rcs_step_async(h, d.secs, d.nanos, N.RCS_STEP_NO_COMMIT))
-        N.check(h, lib.rcs_read_agents(h, N.RCS_ORDER_ID, n, None, *[o[0].ctypes.data_as(N.c_f64p) for o in outs],
-                                       None, C.byref(out_n)))
+        N.check(h, lib.rcs_read_agents_async(h, N.RCS_ORDER_ID, n, None, *[o[0].ctypes.data_as(N.c_f64p) for o in outs],
+                                             C.byref(out_n)))
 
     for _ in range(warmup):
         one()
+    N.check(h, lib.rcs_read_wait(h))
     dist.barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
         one()
+    N.check(h, lib.rcs_read_wait(h))
     dist.barrier()
     t1 = time.perf_counter()
     t = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
@@ -231,4 +234,4 @@ def run_e2e(sim, scene, steps: int, warmup: int, dist, torch) -> dict:
     return {"value": tot.item() * steps / t.item(), "unit": "agent-steps/s",
             "h2d_bytes_per_step": int(16 * tot.item()), "d2h_bytes_per_step": int(32 * tot.item()), "steps": steps,
             "path": "per rank: rcs_set_preferred_velocity(pinned host) + rcs_step_async + "
-                    "rcs_read_agents(ORDER_ID, pinned host); max over ranks of the wall time"}
+                    "rcs_read_agents_async(ORDER_ID, pinned host); max over ranks of the wall time"}
