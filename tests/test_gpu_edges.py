@@ -115,3 +115,29 @@ def test_zero_dt_and_nan_state_behave_like_the_reference():
     assert np.isnan(a["x"][2]) and np.isnan(b["x"][2])
     assert np.allclose(a["x"][:2], b["x"][:2], rtol=1e-9) and np.allclose(a["y"], b["y"], rtol=1e-9)
     assert g.stats().nonfinite_count == 1 and g.stats().oob_count == 0
+
+
+def test_async_read_back_returns_the_same_bits_as_the_blocking_read():
+    from rmf_crowdsim_b200 import scenes as SC
+
+    scene = SC.uniform_crowd(40, "lane", margin=8.0, seed=2)
+    sim = SC.build_simulation(scene)
+    lib, h, n = sim._lib, sim._h, scene.n
+    bufs = [np.zeros(n) for _ in range(4)]
+    ids = np.zeros(n, dtype=np.uint64)
+    out_n = C.c_uint64()
+    for step in range(3):
+        sim.step_async(R.Duration(*scene.dt))
+        N.check(h, lib.rcs_read_agents_async(h, N.RCS_ORDER_ID, n, ids.ctypes.data_as(N.c_u64p),
+                                             *[b.ctypes.data_as(N.c_f64p) for b in bufs], C.byref(out_n)))
+        sim.step_async(R.Duration(*scene.dt))  # enqueued while the copies of the previous step may still run
+        N.check(h, lib.rcs_read_wait(h))
+        snap = [b.copy() for b in bufs]
+        # the blocking read now sees the state one step later; rewind by comparing with a second simulation
+        ref = SC.build_simulation(scene)
+        for _ in range(2 * step + 1):
+            ref.step(R.Duration(*scene.dt))
+        st = ref.read_state()
+        assert out_n.value == n and np.array_equal(ids, st["id"])
+        for b, k in zip(snap, ("x", "y", "vx", "vy")):
+            assert np.array_equal(b.view(np.uint64), st[k].view(np.uint64)), (step, k)
