@@ -86,6 +86,9 @@ struct rcs_sim {
   uint32_t* keep = nullptr;      // churn: 0 = the entry leaves (sink reached, migrated, ghost); dropped by the next sort
   bool cur_has_dead = false;     // `cur` holds entries with keep = 0 (compacted lazily, at rcs_sync)
   uint64_t tile_sums_cap = 0;
+  // cells this handle indexes: the whole grid, or on a strip the columns it owns plus the halo (a multiple of 4
+  // at the lower end: the scan kernels use 16-byte accesses).  cell_start[cell_hi] = number of sorted agents.
+  uint64_t cell_lo = 0, cell_hi = 0;
   uint32_t* cnt = nullptr;       // device counters CNT_*
   uint32_t* h_cnt = nullptr;     // pinned copy
   bool cnt_dirty = true;         // host changed n: cnt[CNT_CUR] must be rewritten before the next step

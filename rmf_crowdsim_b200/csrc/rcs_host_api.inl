@@ -47,6 +47,8 @@ int rcs_sim_create(const rcs_sim_desc* desc, rcs_sim** out) {
   g.len = g.nx * ny;
   g.x_max = (g.len == 0 || g.nx == 0) ? -1 : (int64_t)((g.len - 1) / g.nx);
   g.inv_res = 1.0 / desc->cell_size;
+  s->cell_lo = 0;
+  s->cell_hi = g.len;
   if (s->cap >= 0xfffffff0ull) {
     g_create_error = "capacity must be < 2^32";
     delete s;

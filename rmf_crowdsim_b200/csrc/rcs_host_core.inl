@@ -185,11 +185,13 @@ static int upload_counts(rcs_sim* s) {
 
 // A1/A2 of SURVEY.md section 8a.  Bins the agents [first, cnt[CNT_TOT]) of `cur` into the histogram
 // (which the caller has zeroed, or which already holds the owned agents of a strip).
-static int bin_agents(rcs_sim* s, uint32_t n_ub, const uint32_t* first) {
+static int bin_agents(rcs_sim* s, uint32_t n_ub, const uint32_t* first, uint32_t launch_n = 0) {
   if (!n_ub) return RCS_OK;
-  bin_count_kernel<<<blocks_for(n_ub, 256), 256, 0, s->stream>>>(s->grid, n_ub, first, s->cnt + CNT_TOT, s->cur.x,
+  if (!launch_n) launch_n = n_ub;  // threads to launch: fewer than n_ub when only the tail behind *first is binned
+  bin_count_kernel<<<blocks_for(launch_n, 256), 256, 0, s->stream>>>(s->grid, n_ub, first, s->cnt + CNT_TOT, s->cur.x,
                                                                  s->cur.y, s->cur_has_dead ? s->keep : nullptr,
-                                                                 s->cellid, s->cell_count, s->d_status);
+                                                                 s->cellid, s->cell_count, s->cell_lo, s->cell_hi,
+                                                                 s->d_status);
   s->launches += 1;
   CU_TRY(s, cudaGetLastError());
   return RCS_OK;
@@ -197,20 +199,27 @@ static int bin_agents(rcs_sim* s, uint32_t n_ub, const uint32_t* first) {
 
 // Histogram -> exclusive scan -> permutation scatter -> ascending-id order inside each cell -> physical
 // reorder of `cur` into `srt`.  cell_start[len] is the number of sorted (in-bounds) agents.
+static const uint32_t* n_sorted_ptr(const rcs_sim* s) { return s->cell_start + s->cell_hi; }
+
+static int clear_histogram(rcs_sim* s) {
+  CU_TRY(s, cudaMemsetAsync(s->cell_count + s->cell_lo, 0, (s->cell_hi - s->cell_lo + 1) * sizeof(uint32_t), s->stream));
+  return RCS_OK;
+}
+
 static int sort_into_srt(rcs_sim* s, uint32_t n_ub) {
-  const uint64_t len = s->grid.len;
-  int rc = exclusive_scan(s, s->cell_count, len, s->cell_start, s->cursor);
+  const uint64_t lo = s->cell_lo, hi = s->cell_hi, len = hi - lo;
+  int rc = exclusive_scan(s, s->cell_count + lo, len, s->cell_start + lo, s->cursor + lo);
   if (rc) return rc;
   if (n_ub) {
     scatter_perm_kernel<<<blocks_for(n_ub, 256), 256, 0, s->stream>>>(n_ub, s->cnt + CNT_TOT, s->cellid, s->cursor,
                                                                       s->perm, s->d_status);
     if (len)
-      sort_cells_by_id_kernel<<<blocks_for(len, 128), 128, 0, s->stream>>>(len, s->cell_start, s->cur.id, s->perm,
+      sort_cells_by_id_kernel<<<blocks_for(len, 128), 128, 0, s->stream>>>(lo, hi, s->cell_start, s->cur.id, s->perm,
                                                                            s->big_list, 4096, s->d_status);
-    sort_big_cells_kernel<<<148, 1024, 0, s->stream>>>(len, s->cell_start, s->cur.id, s->perm, s->slow_list, s->big_list,
-                                                     4096, s->d_status);
+    sort_big_cells_kernel<<<148, 1024, 0, s->stream>>>(lo, hi, s->cell_start, s->cur.id, s->perm, s->slow_list,
+                                                       s->big_list, 4096, s->d_status);
     gather_sorted_kernel<<<blocks_for(n_ub, 256), 256, 0, s->stream>>>(
-        n_ub, s->perm, s->cur, s->srt, s->cellid, s->strip.enabled ? s->srt_cell : nullptr, s->cell_start + len,
+        n_ub, s->perm, s->cur, s->srt, s->cellid, s->strip.enabled ? s->srt_cell : nullptr, n_sorted_ptr(s),
         s->grid, s->cell_start, s->d_groups, s->d_groups ? s->slices : nullptr, s->d_status);
     s->launches += 4;
   }
@@ -224,7 +233,8 @@ static int build_index(rcs_sim* s) {
   if (rc) return rc;
   rc = upload_counts(s);
   if (rc) return rc;
-  CU_TRY(s, cudaMemsetAsync(s->cell_count, 0, (s->grid.len + 1) * sizeof(uint32_t), s->stream));
+  rc = clear_histogram(s);
+  if (rc) return rc;
   rc = bin_agents(s, s->n, nullptr);
   if (rc) return rc;
   return sort_into_srt(s, s->n);
@@ -281,7 +291,7 @@ static int drain_kevents(rcs_sim* s) {
 // Undo a failed step on a strip: the snapshot in `cur` (sorted, ghosts included) is reduced to the agents
 // this rank owns.
 static int rollback_owned(rcs_sim* s, uint32_t n_tot) {
-  const uint32_t* n_sorted = s->cell_start + s->grid.len;
+  const uint32_t* n_sorted = n_sorted_ptr(s);
   role_keep_kernel<<<blocks_for(n_tot, 256), 256, 0, s->stream>>>(n_tot, n_sorted, s->srt_cell, (uint32_t)s->grid.nx,
                                                                   s->strip, s->cellid);
   s->launches += 1;
@@ -355,7 +365,7 @@ static int do_sync(rcs_sim* s) {
     uint64_t k = steps_done - s->steps_done_at_sync;
     // the sorted snapshot of the failed step holds cell_start[len] entries (all live: the sort dropped the rest)
     uint32_t n_snapshot = 0;
-    CU_TRY(s, cudaMemcpy(&n_snapshot, s->cell_start + s->grid.len, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CU_TRY(s, cudaMemcpy(&n_snapshot, n_sorted_ptr(s), sizeof(uint32_t), cudaMemcpyDeviceToHost));
     if (k < s->pending.size()) {
       const PendingStep& p = s->pending[k];
       if (p.snapshot_in_srt) {

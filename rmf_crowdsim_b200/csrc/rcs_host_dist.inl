@@ -157,6 +157,13 @@ static int strip_halo_width(rcs_sim* s) {
     return RCS_ERR_HALO;
   }
   s->halo_width = (uint32_t)w;
+  s->strip.reach = (uint32_t)reach;
+  // index only the columns [c0 - W, c1 + W] : every query of an owned or ring agent stays inside [c0 - W, c1 + W);
+  // the extra column keeps the aliased reads of top-row queries (which the step kernel refuses) defined
+  const uint64_t col_lo = s->strip.c0 > w ? s->strip.c0 - w : 0;
+  const uint64_t col_hi = std::min<uint64_t>((uint64_t)s->strip.c1 + w + 1, strip_columns(s));
+  s->cell_lo = (col_lo * s->grid.nx) & ~3ull;
+  s->cell_hi = std::min<uint64_t>(col_hi * s->grid.nx, s->grid.len);
   return RCS_OK;
 }
 

@@ -76,7 +76,7 @@ static StepArgs make_step_args(rcs_sim* s, const AgentArrays& in, const AgentArr
   StepArgs a{};
   a.grid = s->grid;
   a.n = n_ub;
-  a.n_sorted = s->cell_start + s->grid.len;
+  a.n_sorted = n_sorted_ptr(s);
   a.in = in;
   a.cell_start = s->cell_start;
   a.groups = s->d_groups;
@@ -164,13 +164,14 @@ static int step_phase_a(rcs_sim* s, double dt) {
   }
   if (s->strip.enabled) {
     s->n_ub = (uint32_t)s->cap;
-    rc = strip_halo_width(s);
+    rc = strip_halo_width(s);  // also narrows [cell_lo, cell_hi) to the strip and its halo
     if (rc) return rc;
     // the neighbours must have fetched the previous step's send buffers (single-process transport)
     for (rcs_sim* nb : s->local_group)
       if (nb && nb != s && std::abs(nb->rank - s->rank) == 1 && nb->ev_copied)
         CU_TRY(s, cudaStreamWaitEvent(s->stream, nb->ev_copied, 0));
-    CU_TRY(s, cudaMemsetAsync(s->cell_count, 0, (s->grid.len + 1) * sizeof(uint32_t), s->stream));
+    rc = clear_histogram(s);
+    if (rc) return rc;
     rc = bin_agents(s, s->n_ub, nullptr);
     if (rc) return rc;
     const int has_l = s->rank > 0, has_r = s->rank + 1 < s->world;
@@ -216,9 +217,10 @@ static int step_phase_b(rcs_sim* s, double dt, uint32_t flags) {
       halo_unpack_kernel<<<blocks_for(ghosts_ub, 256), 256, 0, s->stream>>>(
           s->cur, s->keep, (uint32_t)s->cap, s->recv_l.buf, s->recv_r.buf, has_l, has_r, s->cnt, s->d_status);
       s->launches += 1;
-      rc = bin_agents(s, n_ub, s->cnt + CNT_CUR);
+      rc = bin_agents(s, n_ub, s->cnt + CNT_CUR, ghosts_ub);
     } else {
-      CU_TRY(s, cudaMemsetAsync(s->cell_count, 0, (s->grid.len + 1) * sizeof(uint32_t), s->stream));
+      rc = clear_histogram(s);
+      if (rc) return rc;
       rc = bin_agents(s, n_ub, nullptr);
     }
     if (rc) return rc;
@@ -237,7 +239,7 @@ static int step_phase_b(rcs_sim* s, double dt, uint32_t flags) {
       if (rc) return rc;
       uint32_t total = 0, n_sorted = 0;
       CU_TRY(s, cudaMemcpyAsync(&total, s->tr_nbo + n_ub, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-      CU_TRY(s, cudaMemcpyAsync(&n_sorted, s->cell_start + s->grid.len, sizeof(uint32_t), cudaMemcpyDeviceToHost,
+      CU_TRY(s, cudaMemcpyAsync(&n_sorted, n_sorted_ptr(s), sizeof(uint32_t), cudaMemcpyDeviceToHost,
                                 s->stream));
       CU_TRY(s, cudaStreamSynchronize(s->stream));
       if (total > s->tr_nbids_cap) {
@@ -277,7 +279,7 @@ static int step_phase_b(rcs_sim* s, double dt, uint32_t flags) {
     }
   }
   end_step_kernel<<<1, 1, 0, s->stream>>>(s->d_status, no_commit ? 0 : 1, s->d_steps_done,
-                                          churned ? s->cnt + CNT_CUR : nullptr, s->cell_start + s->grid.len);
+                                          churned ? s->cnt + CNT_CUR : nullptr, n_sorted_ptr(s));
   s->launches += 1;
   CU_TRY(s, cudaGetLastError());
   if (churned) s->cur_has_dead = true;

@@ -52,7 +52,8 @@ struct StripDev {
   uint32_t enabled;
   uint32_t c0, c1, h;   // own columns [c0, c1); ring width h (columns advanced redundantly on both sides)
   uint32_t lc0, rc1;    // the left neighbour owns [lc0, c0), the right one [c1, rc1)
-  uint32_t pad_[2];
+  uint32_t reach;       // rows / columns a radius query can touch beyond the agent's own cell
+  uint32_t pad_;
 };
 
 struct AgentArrays {
@@ -77,7 +78,8 @@ constexpr uint32_t CELL_DEAD = 0xffffffffu;
 __global__ void bin_count_kernel(GridDev g, uint32_t n_ub, const uint32_t* __restrict__ first,
                                  const uint32_t* __restrict__ last, const double* __restrict__ x,
                                  const double* __restrict__ y, const uint32_t* __restrict__ keep,
-                                 uint32_t* __restrict__ cellid, uint32_t* __restrict__ cell_count, DevStatus* status) {
+                                 uint32_t* __restrict__ cellid, uint32_t* __restrict__ cell_count, uint64_t cell_lo,
+                                 uint64_t cell_hi, DevStatus* status) {
   if (status->failed) return;
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x + (first ? *first : 0u);
   if (i >= n_ub || i >= *last) return;
@@ -87,6 +89,13 @@ __global__ void bin_count_kernel(GridDev g, uint32_t n_ub, const uint32_t* __res
   }
   uint64_t idx;
   if (location_to_index(g, x[i], y[i], idx)) {
+    if (idx < cell_lo || idx >= cell_hi) {
+      // strips index only the cells of their own columns and halo; an agent elsewhere (possible only through the
+      // row aliasing of location_hash_2d.rs:59 far above the grid) cannot be handled by this rank
+      cellid[i] = CELL_DEAD;
+      atomicAdd(&status->halo_err, 1u);
+      return;
+    }
     cellid[i] = (uint32_t)idx;
     atomicAdd(&cell_count[idx], 1u);
   } else {
@@ -237,12 +246,12 @@ __global__ void scatter_perm_kernel(uint32_t n_ub, const uint32_t* __restrict__ 
 // Canonical order inside a cell = ascending agent id (the reference's HashSet order is random per
 // process).  One thread per cell; insertion sort of the cell's permutation
 // slice keyed by id.  Cells larger than SORT_LOCAL_MAX go to the block-wide rank sorter.
-__global__ void sort_cells_by_id_kernel(uint64_t len, const uint32_t* __restrict__ cell_start,
+__global__ void sort_cells_by_id_kernel(uint64_t cell_lo, uint64_t cell_hi, const uint32_t* __restrict__ cell_start,
                                         const uint64_t* __restrict__ id, uint32_t* __restrict__ perm,
                                         uint32_t* __restrict__ big_list, uint32_t big_cap, DevStatus* status) {
   if (status->failed) return;
-  uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= len) return;
+  uint64_t c = cell_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cell_hi) return;
   uint32_t s = cell_start[c], e = cell_start[c + 1];
   uint32_t m = e - s;
   if (m < 2) return;
@@ -303,7 +312,8 @@ __device__ __forceinline__ void sort_one_big_cell(uint32_t s, uint32_t e, const 
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(1024) sort_big_cells_kernel(uint64_t len, const uint32_t* __restrict__ cell_start,
+__global__ void __launch_bounds__(1024) sort_big_cells_kernel(uint64_t cell_lo, uint64_t cell_hi,
+                                                              const uint32_t* __restrict__ cell_start,
                                                               const uint64_t* __restrict__ id,
                                                               uint32_t* __restrict__ perm,
                                                               uint32_t* __restrict__ scratch,
@@ -318,7 +328,7 @@ __global__ void __launch_bounds__(1024) sort_big_cells_kernel(uint64_t len, cons
       sort_one_big_cell(cell_start[c], cell_start[c + 1], id, perm, scratch, skeys);
     }
   } else {
-    for (uint64_t c = blockIdx.x; c < len; c += gridDim.x) {  // block-uniform: every thread sees the same bounds
+    for (uint64_t c = cell_lo + blockIdx.x; c < cell_hi; c += gridDim.x) {  // block-uniform bounds
       const uint32_t cs = cell_start[c], ce = cell_start[c + 1];
       if (ce - cs > SORT_LOCAL_MAX) sort_one_big_cell(cs, ce, id, perm, scratch, skeys);
     }
@@ -656,6 +666,9 @@ __device__ __forceinline__ void integrate_and_store(const StepArgs& a, uint32_t 
                                          : (ocx + a.strip.h >= a.strip.c1 && x_idx < a.strip.rc1);
       if (!ok) atomicAdd(&a.status->halo_err, 1u);
     }
+    // a query from the top `reach` rows of the grid runs over into the NEXT column's bottom cells (y_idx >= n_x
+    // aliases, location_hash_2d.rs:74-85), which may lie beyond this rank's halo: refuse rather than be inexact
+    if (own && inb && y_idx + a.strip.reach >= a.grid.nx) atomicAdd(&a.status->halo_err, 1u);
     keep = keep && mine;
   }
   if (a.no_commit) keep = own;  // the pre-step snapshot stays: this rank keeps exactly what it owned
