@@ -677,17 +677,14 @@ __device__ __forceinline__ void integrate_and_store(const StepArgs& a, uint32_t 
 
 __device__ __forceinline__ void warp_stats(const StepArgs& a, uint32_t cand, uint32_t nbc, uint32_t finite) {
   if (!a.collect_stats) return;
-  unsigned long long c = cand, nb = nbc, ft = finite;
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    c += __shfl_down_sync(0xffffffffu, c, d);
-    nb += __shfl_down_sync(0xffffffffu, nb, d);
-    ft += __shfl_down_sync(0xffffffffu, ft, d);
-  }
+  // hardware warp reductions; a per-agent count above 2^27 would be needed to overflow 32 bits
+  const uint32_t c = __reduce_add_sync(0xffffffffu, cand);
+  const uint32_t nb = __reduce_add_sync(0xffffffffu, nbc);
+  const uint32_t ft = __reduce_add_sync(0xffffffffu, finite);
   if ((threadIdx.x & 31) == 0) {
-    if (c) atomicAdd(&a.status->candidate_total, c);
-    if (nb) atomicAdd(&a.status->neighbour_total, nb);
-    if (ft) atomicAdd(&a.status->finite_tti, ft);
+    if (c) atomicAdd(&a.status->candidate_total, (unsigned long long)c);
+    if (nb) atomicAdd(&a.status->neighbour_total, (unsigned long long)nb);
+    if (ft) atomicAdd(&a.status->finite_tti, (unsigned long long)ft);
   }
 }
 
