@@ -264,6 +264,9 @@ static void launch_step_kernel(rcs_sim* s, const StepArgs& a, uint32_t n_ub, boo
     // agents with a stencil wider than three columns or very crowded cells (device-side list)
     step_slow_kernel<<<148 * 2, 128, 0, s->stream>>>(a);
     s->launches += 2;
+  } else if (!sorted_input && s->opt_step_kernel != 1) {
+    step_stream_kernel<<<blocks_for((n_ub + 1) / 2, 256), 256, 0, s->stream>>>(a);  // NoLocalPlan only, no churn
+    s->launches += 1;
   } else {
     step_kernel<<<blocks_for(n_ub, 128), 128, 0, s->stream>>>(a);
     s->launches += 1;

@@ -734,6 +734,88 @@ __global__ void __launch_bounds__(128) step_kernel(StepArgs a) {
   warp_stats(a, cand, nbc, finite);
 }
 
+// NoLocalPlan-only crowds without churn (no_local_plan.rs:10-17: the local planner returns the recommended
+// velocity, no query can influence the result): lib.rs:259-347 degenerates to a stream over the agents in storage
+// order -- high-level velocity, explicit Euler, add_or_update's bounds check.  Two agents per thread with 16-byte
+// accesses; 64 algorithmic bytes per agent, HBM-bound.  Same operations as step_one_agent.
+__device__ __forceinline__ void stream_one(const StepArgs& a, const GroupDev& g, double px, double py, uint64_t id,
+                                           double hx, double hy, double& nx, double& ny, double& velx, double& vely) {
+  velx = 0.0;
+  vely = 0.0;
+  switch (g.hl_kind) {
+    case HL_CONSTANT:
+      velx = g.hl_vx;
+      vely = g.hl_vy;
+      break;
+    case HL_PARITY:
+      velx = (id & 1ull) == 0ull ? -g.hl_vx : g.hl_vx;
+      vely = (id & 1ull) == 0ull ? -g.hl_vy : g.hl_vy;
+      break;
+    case HL_HOST:
+      if (hx == hx) {  // NaN in x encodes None
+        velx = hx;
+        vely = hy;
+      }
+      break;
+    default:
+      break;
+  }
+  nx = px + velx * a.dt;
+  ny = py + vely * a.dt;
+  const uint64_t x_idx = f64_as_usize(div_floor(nx - a.grid.offx, a.grid));
+  const uint64_t y_idx = f64_as_usize(div_floor(ny - a.grid.offy, a.grid));
+  if (!(x_idx * a.grid.nx + y_idx < a.grid.len)) {
+    atomicAdd(&a.status->oob_count, 1u);
+    atomicMin(&a.status->first_oob_id, (unsigned long long)id);
+  }
+  if (!(isfinite(nx) && isfinite(ny) && isfinite(velx) && isfinite(vely))) atomicAdd(&a.status->nonfinite_count, 1u);
+}
+
+__global__ void __launch_bounds__(256) step_stream_kernel(StepArgs a) {
+  const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) * 2u;
+  if (i >= a.n) return;
+  const bool pair = i + 1u < a.n;  // every array holds at least a.n entries (a.n is even-padded by cudaMalloc)
+  double2 p_x, p_y, h_x = make_double2(0.0, 0.0), h_y = make_double2(0.0, 0.0);
+  ulonglong2 p_id;
+  uint2 p_g;
+  if (pair) {
+    p_x = *reinterpret_cast<const double2*>(a.in.x + i);
+    p_y = *reinterpret_cast<const double2*>(a.in.y + i);
+    p_id = *reinterpret_cast<const ulonglong2*>(a.in.id + i);
+    p_g = *reinterpret_cast<const uint2*>(a.in.grp + i);
+    if (a.in.pvx) {
+      h_x = *reinterpret_cast<const double2*>(a.in.pvx + i);
+      h_y = *reinterpret_cast<const double2*>(a.in.pvy + i);
+    }
+  } else {
+    p_x = make_double2(a.in.x[i], 0.0);
+    p_y = make_double2(a.in.y[i], 0.0);
+    p_id = make_ulonglong2(a.in.id[i], 0ull);
+    p_g = make_uint2(a.in.grp[i], 0u);
+    if (a.in.pvx) {
+      h_x.x = a.in.pvx[i];
+      h_y.x = a.in.pvy[i];
+    }
+  }
+  if (a.status->failed) return;
+  const uint32_t n_live = *a.n_sorted;
+  if (i >= n_live) return;
+  double2 o_x = p_x, o_y = p_y, o_vx = make_double2(0.0, 0.0), o_vy = make_double2(0.0, 0.0);
+  stream_one(a, a.groups[p_g.x], p_x.x, p_y.x, p_id.x, h_x.x, h_y.x, o_x.x, o_y.x, o_vx.x, o_vy.x);
+  if (pair && i + 1u < n_live) {
+    stream_one(a, a.groups[p_g.y], p_x.y, p_y.y, p_id.y, h_x.y, h_y.y, o_x.y, o_y.y, o_vx.y, o_vy.y);
+    *reinterpret_cast<double2*>(a.ox + i) = o_x;
+    *reinterpret_cast<double2*>(a.oy + i) = o_y;
+    *reinterpret_cast<double2*>(a.ovx + i) = o_vx;
+    *reinterpret_cast<double2*>(a.ovy + i) = o_vy;
+  } else {
+    a.ox[i] = o_x.x;
+    a.oy[i] = o_y.x;
+    a.ovx[i] = o_vx.x;
+    a.ovy[i] = o_vy.x;
+  }
+}
+
 // Finishes the agents the warp-cooperative kernel put on the slow list (stencil wider than three
 // columns or more than SW_MAXC candidates).  Grid-stride over the device-side count.
 __global__ void __launch_bounds__(128) step_slow_kernel(StepArgs a) {

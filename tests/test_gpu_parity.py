@@ -302,3 +302,23 @@ def test_more_oversized_cells_than_the_big_cell_list_holds():
     key = cells.astype(np.uint64) * np.uint64(1 << 32) + st["id"]
     assert np.all(key[1:] > key[:-1])
     assert len(st["id"]) == len(xy) and sim.stats().oob_count == 0
+
+
+@pytest.mark.parametrize("n_side", [31, 64])
+def test_streaming_kernel_of_no_local_plan_crowds_matches_the_generic_kernel_and_the_oracle(n_side):
+    """NoLocalPlan-only crowds take step_stream_kernel (two agents per thread, no index): same bits as the
+    thread-per-agent kernel and as the oracle (only IEEE mul/add are involved); odd agent counts hit the tail."""
+    scene = SC.uniform_crowd(n_side, "shuffled", margin=8.0, seed=6, lp=("none",))
+    a = SC.build_simulation(scene)
+    b = SC.build_simulation(scene)
+    b.set_option(R._native.RCS_OPT_STEP_KERNEL, 1)
+    o = P.build_oracle(scene)
+    # a host-evaluated planner for half of the agents (None for a few of them)
+    for _ in range(5):
+        P.step_both(a, o, scene)
+        b.step(R.Duration(*scene.dt))
+    sa, sb, so = a.read_state(), b.read_state(), o.read_state()
+    for k in ("x", "y", "vx", "vy"):
+        assert np.array_equal(sa[k].view(np.uint64), sb[k].view(np.uint64)), k
+        assert np.array_equal(sa[k].view(np.uint64), so[k].view(np.uint64)), k
+    assert a.launch_count() < b.launch_count() + 100  # both ran; no index was built on either path
