@@ -341,6 +341,34 @@ __global__ void __launch_bounds__(1024) sort_big_cells_kernel(uint64_t cell_lo, 
 // location_hash_2d.rs:74-122), as {start0, start1, start2, len0 | len1 << 8 | len2 << 16 | ok << 24}.
 // ok = 0: the stencil is wider than three columns (the agent takes the sequential routine); lengths saturate
 // at 255.
+__device__ __forceinline__ uint4 query_slices(const GridDev& g, const uint32_t* __restrict__ cell_start,
+                                              const GroupDev& gr, double px, double py) {
+  uint4 sl = make_uint4(0u, 0u, 0u, 0u);
+  if (gr.lp_kind == LP_ZANLUNGO) {
+    int64_t left, right, bottom, top;
+    get_bounds(g, gr.eyesight, px, py, left, right, bottom, top);
+    if (left < 0) left = 0;
+    if (right > g.x_max) right = g.x_max;
+    if (right - left <= 2) {
+      uint32_t st[3] = {0, 0, 0}, ln[3] = {0, 0, 0};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        uint64_t c_lo, c_hi;
+        if (left + c <= right && column_cell_range(g, left + c, bottom, top, c_lo, c_hi)) {
+          st[c] = cell_start[c_lo];
+          const uint32_t l = cell_start[c_hi + 1] - st[c];
+          ln[c] = l > 255u ? 255u : l;
+        }
+      }
+      sl = make_uint4(st[0], st[1], st[2], ln[0] | (ln[1] << 8) | (ln[2] << 16) | (1u << 24));
+    }
+  }
+  return sl;
+}
+
+// Two sorted slots per thread.  The arrays being gathered are last step's sorted output and agents rarely change
+// cell, so perm[k], perm[k+1] are usually an aligned consecutive pair: then every array moves with 16-byte
+// accesses (8-byte for the two 4-byte arrays); otherwise element by element.
 __global__ void gather_sorted_kernel(uint32_t n, const uint32_t* __restrict__ perm, AgentArrays cur,
                                      AgentArrays srt, const uint32_t* __restrict__ cellid,
                                      uint32_t* __restrict__ srt_cell, const uint32_t* __restrict__ n_sorted,
@@ -348,46 +376,58 @@ __global__ void gather_sorted_kernel(uint32_t n, const uint32_t* __restrict__ pe
                                      const GroupDev* __restrict__ groups, uint4* __restrict__ slices,
                                      const DevStatus* status) {
   if (status->failed) return;
-  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n || k >= *n_sorted) return;
-  uint32_t i = perm[k];
-  if (srt_cell) srt_cell[k] = cellid[i];
-  const double px = cur.x[i], py = cur.y[i];
-  const uint32_t grp = cur.grp[i];
-  srt.x[k] = px;
-  srt.y[k] = py;
-  srt.vx[k] = cur.vx[i];
-  srt.vy[k] = cur.vy[i];
-  srt.id[k] = cur.id[i];
-  srt.grp[k] = grp;
-  srt.wp[k] = cur.wp[i];
-  if (cur.pvx) {
-    srt.pvx[k] = cur.pvx[i];
-    srt.pvy[k] = cur.pvy[i];
-  }
-  if (slices) {
-    uint4 sl = make_uint4(0u, 0u, 0u, 0u);
-    const GroupDev& gr = groups[grp];
-    if (gr.lp_kind == LP_ZANLUNGO) {
-      int64_t left, right, bottom, top;
-      get_bounds(g, gr.eyesight, px, py, left, right, bottom, top);
-      if (left < 0) left = 0;
-      if (right > g.x_max) right = g.x_max;
-      if (right - left <= 2) {
-        uint32_t st[3] = {0, 0, 0}, ln[3] = {0, 0, 0};
+  const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) * 2u;
+  const uint32_t lim = min(n, *n_sorted);
+  if (k >= lim) return;
+  const bool two = k + 1u < lim;
+  const uint32_t i0 = perm[k];
+  const uint32_t i1 = two ? perm[k + 1u] : 0u;
+  double px[2], py[2];
+  uint32_t grp[2];
+  if (two && i1 == i0 + 1u && (i0 & 1u) == 0u) {
+    const double2 vx2 = *reinterpret_cast<const double2*>(cur.x + i0);
+    const double2 vy2 = *reinterpret_cast<const double2*>(cur.y + i0);
+    const uint2 g2 = *reinterpret_cast<const uint2*>(cur.grp + i0);
+    *reinterpret_cast<double2*>(srt.x + k) = vx2;
+    *reinterpret_cast<double2*>(srt.y + k) = vy2;
+    *reinterpret_cast<double2*>(srt.vx + k) = *reinterpret_cast<const double2*>(cur.vx + i0);
+    *reinterpret_cast<double2*>(srt.vy + k) = *reinterpret_cast<const double2*>(cur.vy + i0);
+    *reinterpret_cast<ulonglong2*>(srt.id + k) = *reinterpret_cast<const ulonglong2*>(cur.id + i0);
+    *reinterpret_cast<uint2*>(srt.grp + k) = g2;
+    *reinterpret_cast<uint2*>(srt.wp + k) = *reinterpret_cast<const uint2*>(cur.wp + i0);
+    if (cur.pvx) {
+      *reinterpret_cast<double2*>(srt.pvx + k) = *reinterpret_cast<const double2*>(cur.pvx + i0);
+      *reinterpret_cast<double2*>(srt.pvy + k) = *reinterpret_cast<const double2*>(cur.pvy + i0);
+    }
+    if (srt_cell) *reinterpret_cast<uint2*>(srt_cell + k) = *reinterpret_cast<const uint2*>(cellid + i0);
+    px[0] = vx2.x; px[1] = vx2.y;
+    py[0] = vy2.x; py[1] = vy2.y;
+    grp[0] = g2.x; grp[1] = g2.y;
+  } else {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          uint64_t c_lo, c_hi;
-          if (left + c <= right && column_cell_range(g, left + c, bottom, top, c_lo, c_hi)) {
-            st[c] = cell_start[c_lo];
-            const uint32_t l = cell_start[c_hi + 1] - st[c];
-            ln[c] = l > 255u ? 255u : l;
-          }
-        }
-        sl = make_uint4(st[0], st[1], st[2], ln[0] | (ln[1] << 8) | (ln[2] << 16) | (1u << 24));
+    for (int e = 0; e < 2; ++e) {
+      if (e == 1 && !two) break;
+      const uint32_t i = e ? i1 : i0;
+      px[e] = cur.x[i];
+      py[e] = cur.y[i];
+      grp[e] = cur.grp[i];
+      if (srt_cell) srt_cell[k + e] = cellid[i];
+      srt.x[k + e] = px[e];
+      srt.y[k + e] = py[e];
+      srt.vx[k + e] = cur.vx[i];
+      srt.vy[k + e] = cur.vy[i];
+      srt.id[k + e] = cur.id[i];
+      srt.grp[k + e] = grp[e];
+      srt.wp[k + e] = cur.wp[i];
+      if (cur.pvx) {
+        srt.pvx[k + e] = cur.pvx[i];
+        srt.pvy[k + e] = cur.pvy[i];
       }
     }
-    slices[k] = sl;
+  }
+  if (slices) {
+    slices[k] = query_slices(g, cell_start, groups[grp[0]], px[0], py[0]);
+    if (two) slices[k + 1u] = query_slices(g, cell_start, groups[grp[1]], px[1], py[1]);
   }
 }
 
