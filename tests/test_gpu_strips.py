@@ -21,7 +21,7 @@ def _same(a, b):
         assert np.array_equal(a[k], b[k]), k
 
 
-@pytest.mark.parametrize("world", [2, 3, 5])
+@pytest.mark.parametrize("world", [1, 2, 3, 5])
 def test_strips_are_bit_identical_to_one_handle_lane_crowd(world):
     """40 committed steps of the lane-ordered crowd: agents stream across every strip boundary (1.3 m/s,
     cells of 2 m), so migration through the redundant ring is exercised in both directions."""
@@ -36,7 +36,7 @@ def test_strips_are_bit_identical_to_one_handle_lane_crowd(world):
     _same(single.read_state(), grp.read_state())
     assert sum(grp.agent_counts()) == scene.n
     after = [set(sm.read_state()["id"].tolist()) for sm in grp.sims]
-    assert all(a != b for a, b in zip(after, before))  # agents really migrated, in both directions
+    assert world == 1 or all(a != b for a, b in zip(after, before))  # agents really migrated, in both directions
     assert set().union(*after) == set(range(scene.n))
 
 
