@@ -1,0 +1,160 @@
+"""A second, independently written restatement of local_planners/zanlungo.rs -- plain Python floats (IEEE double,
+the platform libm), transcribed line by line from the Rust source -- checked against the C++ oracle's golden
+vectors.  `compute_agent_force`, `right_of_way_vel`, `slerp` and `compute_tti` have no test in the reference; two
+restatements written separately and agreeing to the last bits is the strongest pin available without a Rust
+toolchain."""
+import math
+import os
+
+import numpy as np
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+INF = float("inf")
+
+
+def _norm(v):
+    return math.sqrt(v[0] * v[0] + v[1] * v[1])
+
+
+def _dot(a, b):
+    return a[0] * b[0] + a[1] * b[1]
+
+
+def slerp(t, p0, p1, sin_theta):  # zanlungo.rs:23-28
+    theta = math.asin(sin_theta)
+    t0 = math.sin((1.0 - t) * theta) / sin_theta if sin_theta != 0.0 else float("nan")
+    t1 = math.sin(t * theta) / sin_theta if sin_theta != 0.0 else float("nan")
+    return (p0[0] * t0 + p1[0] * t1, p0[1] * t0 + p1[1] * t1)
+
+
+class Zanlungo:
+    def __init__(self, agent_scale, obstacle_scale, reaction_time, force_distance, agent_mass, agent_radius):
+        self.agent_scale, self.force_distance = agent_scale, force_distance
+        self.agent_mass, self.agent_radius = agent_mass, agent_radius
+
+    def time_to_collision(self, rel_vel, rel_pos):  # zanlungo.rs:49-74
+        a = _dot(rel_vel, rel_vel)
+        b = 2.0 * _dot(rel_vel, rel_pos)
+        c = _dot(rel_pos, rel_pos) - self.agent_radius * self.agent_radius
+        discriminant = b * b - 4.0 * a * c
+        if discriminant < 0.0:
+            return INF
+        if a == 0.0:  # 0/0 = NaN in Rust: every comparison below is false
+            return INF
+        sq = math.sqrt(discriminant)
+        t0 = (-b - sq) / (2.0 * a)
+        t1 = (-b + sq) / (2.0 * a)
+        if (t0 < 0.0 and t1 > 0.0) or (t1 < 0.0 and t0 > 0.0):
+            return 0.0
+        if t0 < t1 and t0 > 0.0:
+            return t0
+        if t1 > 0.0:
+            return t1
+        return INF
+
+    def right_of_way_vel(self, agent_id, agent_vel, self_pref, other_vel, other_pref, other_priority):  # :173-198
+        row = min(max(float(agent_id) - other_priority, -1.0), 1.0)
+        if row < 0.0:
+            r_2 = math.sqrt(-row)
+            adj = (other_vel[0] + r_2 * (other_pref[0] - other_vel[0]), other_vel[1] + r_2 * (other_pref[1] - other_vel[1]))
+            return -r_2, agent_vel, adj
+        if row > 0.0:
+            r_2 = math.sqrt(row)
+            vel = (agent_vel[0] + r_2 * (self_pref[0] - agent_vel[0]), agent_vel[1] + r_2 * (self_pref[1] - agent_vel[1]))
+            return r_2, vel, other_vel
+        return 0.0, agent_vel, other_vel
+
+    def compute_agent_force(self, agent, other, t_i):  # :93-170; agent = (id, pos, vel, pref)
+        aid, apos, avel, apref = agent
+        oid, opos, ovel, opref = other
+        weight, my_vel, other_vel = self.right_of_way_vel(aid, avel, apref, ovel, opref, float(oid))
+        weight = 1.0 - weight
+        fut = (apos[0] + my_vel[0] * t_i, apos[1] + my_vel[1] * t_i)
+        ofut = (opos[0] + other_vel[0] * t_i, opos[1] + other_vel[1] * t_i)
+        d_ij = (fut[0] - ofut[0], fut[1] - ofut[1])
+        dist = _norm(d_ij)
+        if weight > 1.0:
+            interpolate = True
+            perp = (0.0, 0.0)
+            if _norm(opref) < 0.0001:
+                crp = (apos[0] - opos[0], apos[1] - opos[1])
+                perp = (-crp[1], crp[0])
+                if _dot(perp, avel) < 0.0:
+                    perp = (-perp[0], -perp[1])
+            else:
+                if _dot(opref, d_ij) > 0.0:
+                    perp = (-opref[1], opref[0])
+                    if _dot(perp, d_ij) < 0.0:
+                        perp = (-perp[0], -perp[1])
+                else:
+                    interpolate = False
+            if interpolate:
+                sin_theta = perp[0] * d_ij[1] - perp[1] * d_ij[0]
+                if sin_theta < 0.0:
+                    sin_theta = -sin_theta
+                if sin_theta > 1.0:
+                    sin_theta = 1.0
+                d_ij = slerp(weight - 1.0, d_ij, perp, sin_theta)
+        if dist > _norm((fut[0] - ofut[0], fut[1] - ofut[1])):
+            return (0.0, 0.0)
+        n = _norm(d_ij)
+        dn = (d_ij[0] / n, d_ij[1] / n) if n != 0.0 else (float("nan"), float("nan"))
+        surface_dist = dist - self.agent_radius * 2.0
+        rv = (my_vel[0] - other_vel[0], my_vel[1] - other_vel[1])
+        magnitude = weight * self.agent_scale * _norm(rv) / t_i
+        if magnitude >= 1e15:
+            magnitude = 1e15
+        s = magnitude * math.exp(-surface_dist / self.force_distance)
+        return (dn[0] * s, dn[1] * s)
+
+
+def _rel(a, b, scale=0.0):
+    return abs(a - b) / max(abs(a), abs(b), scale, 1e-300)
+
+
+def test_pair_table_agrees_with_the_independent_restatement():
+    g = np.load(os.path.join(G, "pair_table.npz"))
+    z = Zanlungo(*g["params"])
+    worst = 0.0
+    for k in range(len(g["t_i"])):
+        a, o = g["agent"][k], g["other"][k]
+        f = z.compute_agent_force((int(g["aid"][k]), (a[0], a[1]), (a[2], a[3]), (a[4], a[5])),
+                                  (int(g["oid"][k]), (o[0], o[1]), (o[2], o[3]), (o[4], o[5])), float(g["t_i"][k]))
+        mag = math.hypot(*g["force"][k])
+        worst = max(worst, _rel(f[0], g["force"][k][0], mag), _rel(f[1], g["force"][k][1], mag))
+    assert worst <= 1e-14
+    z = Zanlungo(1, 1, 0, 1, 1, float(g["ttc_radius"][0]))
+    for k in range(len(g["ttc"])):
+        t = z.time_to_collision(tuple(g["rel_vel"][k]), tuple(g["rel_pos"][k]))
+        assert np.float64(t).view(np.uint64) == g["ttc"][k].view(np.uint64), k  # bit-exact
+
+
+def test_crowd_step_agrees_with_the_independent_restatement():
+    """t_i (compute_tti, :76-91) and the force sum (get_desired_velocity, :201-218) of all 576 agents, recomputed
+    from the golden neighbour lists in list order; neighbours' preferred_vel is (0,0) (lib.rs:57,285)."""
+    g = np.load(os.path.join(G, "crowd_576.npz"))
+    z = Zanlungo(0.05, 1.0, 0.0, 0.5, 1.0, 0.2)
+    xy, v = g["in_xy"], g["in_vxy"]
+    off, nb = g["nb_offsets"].astype(np.int64), g["nb_ids"].astype(np.int64)
+    worst, finite = 0.0, 0
+    for i in range(len(xy)):
+        pref = (-1.3, 0.0) if i % 2 == 0 else (1.3, 0.0)  # parity planner (main.rs:26-29) with v = (1.3, 0)
+        me = (i, (xy[i, 0], xy[i, 1]), (v[i, 0], v[i, 1]), pref)
+        t_i = INF
+        for j in nb[off[i]:off[i + 1]]:
+            ct = z.time_to_collision((v[j, 0] - v[i, 0], v[j, 1] - v[i, 1]), (xy[j, 0] - xy[i, 0], xy[j, 1] - xy[i, 1]))
+            if ct < t_i:
+                t_i = ct
+        assert np.float64(t_i).view(np.uint64) == g["t_i"][i].view(np.uint64), i
+        fx = fy = 0.0
+        if t_i != INF:
+            finite += 1
+            for j in nb[off[i]:off[i + 1]]:
+                f = z.compute_agent_force(me, (int(j), (xy[j, 0], xy[j, 1]), (v[j, 0], v[j, 1]), (0.0, 0.0)), t_i)
+                fx += f[0]
+                fy += f[1]
+        mag = math.hypot(g["fx"][i], g["fy"][i])
+        worst = max(worst, _rel(fx, g["fx"][i], mag), _rel(fy, g["fy"][i], mag))
+        vx, vy = pref[0] + fx * (1.0 / 1.0), pref[1] + fy * (1.0 / 1.0)
+        assert _rel(vx, g["vx"][i], 1.0) <= 1e-14 and _rel(vy, g["vy"][i], 1.0) <= 1e-14
+    assert finite > 100 and worst <= 1e-13
