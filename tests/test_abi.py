@@ -63,3 +63,18 @@ def test_no_device_fails_loudly(gpu_available):
 
     with pytest.raises(R.CrowdsimError):
         R.LocationHash2D(10, 10, 1, (0, 0))
+
+
+def test_rust_sys_crate_declares_only_header_symbols():
+    """bindings/rust/rmf_crowdsim_gpu-sys is written by hand (no Rust toolchain here): at least every function it
+    declares must exist in include/rcs.h, and the per-step entry points a maintainer needs must all be there."""
+    import re
+
+    src = open(os.path.join(ROOT, "bindings", "rust", "rmf_crowdsim_gpu-sys", "src", "lib.rs")).read()
+    rust = set(re.findall(r"pub fn (rcs_[a-z0-9_]+)\(", src))
+    hdr = set(header_symbols())
+    assert rust and rust <= hdr, sorted(rust - hdr)
+    need = {"rcs_sim_create", "rcs_sim_destroy", "rcs_last_error", "rcs_lp_none", "rcs_lp_zanlungo", "rcs_add_agents",
+            "rcs_remove_agents", "rcs_step", "rcs_read_agents", "rcs_poll_events", "rcs_add_source_sink",
+            "rcs_query_radius", "rcs_query_knn", "rcs_index_add_or_update", "rcs_index_remove"}
+    assert need <= rust
