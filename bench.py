@@ -433,8 +433,15 @@ def main():
 
         stream_bench.run(args)
         return
-    if args.gpus == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus == 1 and world == 1:
         run_gpu_single(args)
+    elif world == 1:
+        # `python bench.py --gpus N` without a launcher: start one rank per GPU ourselves (the driver uses torchrun)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"),
+               os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
     else:
         from rmf_crowdsim_b200 import dist_bench
 
