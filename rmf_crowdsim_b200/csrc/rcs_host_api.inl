@@ -248,16 +248,11 @@ static int add_agents_impl(rcs_sim* s, uint64_t n, const uint64_t* ids, const do
   int rc = do_sync(s);
   if (rc) return rc;
   uint32_t grp = find_or_add_group(s, hl, lp, eyesight, source_sink);
-  std::vector<double> hx(n), hy(n), hvx(n, 0.0), hvy(n, 0.0);
+  std::vector<double> hv;  // initial velocities: zero unless given (lib.rs:139)
+  if (!vxy) hv.assign(2 * n, 0.0);
   std::vector<uint64_t> hid(n);
   std::vector<uint32_t> hgrp(n, grp), hwp(n, 0u);
   for (uint64_t k = 0; k < n; ++k) {
-    hx[k] = xy[2 * k];
-    hy[k] = xy[2 * k + 1];
-    if (vxy) {
-      hvx[k] = vxy[2 * k];
-      hvy[k] = vxy[2 * k + 1];
-    }
     if (ids) {
       hid[k] = ids[k];
       s->max_id_plus1 = std::max(s->max_id_plus1, ids[k] + 1);
@@ -268,18 +263,16 @@ static int add_agents_impl(rcs_sim* s, uint64_t n, const uint64_t* ids, const do
   }
   if (!ids) s->max_id_plus1 = std::max(s->max_id_plus1, s->last_alloc_agent_id);
   const uint32_t o = s->n;
-  CU_TRY(s, cudaMemcpy(s->cur.x + o, hx.data(), n * sizeof(double), cudaMemcpyHostToDevice));
-  CU_TRY(s, cudaMemcpy(s->cur.y + o, hy.data(), n * sizeof(double), cudaMemcpyHostToDevice));
-  CU_TRY(s, cudaMemcpy(s->cur.vx + o, hvx.data(), n * sizeof(double), cudaMemcpyHostToDevice));
-  CU_TRY(s, cudaMemcpy(s->cur.vy + o, hvy.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+  // the caller's interleaved (x, y) rows are the device layout
+  CU_TRY(s, cudaMemcpy(s->cur.pos + o, xy, n * sizeof(double2), cudaMemcpyHostToDevice));
+  CU_TRY(s, cudaMemcpy(s->cur.vel + o, vxy ? vxy : hv.data(), n * sizeof(double2), cudaMemcpyHostToDevice));
   CU_TRY(s, cudaMemcpy(s->cur.id + o, hid.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice));
   CU_TRY(s, cudaMemcpy(s->cur.grp + o, hgrp.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
   CU_TRY(s, cudaMemcpy(s->cur.wp + o, hwp.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
-  if (s->cur.pvx) {
+  if (s->cur.pv) {
     const double nan = std::numeric_limits<double>::quiet_NaN();
-    fill_f64_kernel<<<blocks_for(n, 256), 256, 0, s->stream>>>(n, s->cur.pvx + o, nan);
-    fill_f64_kernel<<<blocks_for(n, 256), 256, 0, s->stream>>>(n, s->cur.pvy + o, nan);
-    s->launches += 2;
+    fill_f64_kernel<<<blocks_for(2 * n, 256), 256, 0, s->stream>>>(2 * n, reinterpret_cast<double*>(s->cur.pv + o), nan);
+    s->launches += 1;
     CU_TRY(s, cudaStreamSynchronize(s->stream));
   }
   s->n += (uint32_t)n;
@@ -331,17 +324,12 @@ __global__ void compact_kernel(uint32_t n, const uint32_t* __restrict__ keep, co
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || !keep[i]) return;
   uint32_t k = pos[i];
-  out.x[k] = in.x[i];
-  out.y[k] = in.y[i];
-  out.vx[k] = in.vx[i];
-  out.vy[k] = in.vy[i];
+  out.pos[k] = in.pos[i];
+  out.vel[k] = in.vel[i];
   out.id[k] = in.id[i];
   out.grp[k] = in.grp[i];
   out.wp[k] = in.wp[i];
-  if (in.pvx) {
-    out.pvx[k] = in.pvx[i];
-    out.pvy[k] = in.pvy[i];
-  }
+  if (in.pv) out.pv[k] = in.pv[i];
 }
 
 int rcs_remove_agents(rcs_sim* s, uint64_t m, const uint64_t* ids) {
@@ -418,13 +406,15 @@ int rcs_set_state(rcs_sim* s, uint64_t m, const uint64_t* ids, const double* x, 
   }
   CU_TRY(s, cudaMemsetAsync(s->d_bad, 0, sizeof(unsigned int), s->stream));
   const double* srcs[4] = {x, y, vx, vy};
-  double* dsts[4] = {s->cur.x, s->cur.y, s->cur.vx, s->cur.vy};
+  double* const posd = reinterpret_cast<double*>(s->cur.pos);
+  double* const veld = reinterpret_cast<double*>(s->cur.vel);
+  double* dsts[4] = {posd, posd + 1, veld, veld + 1};  // components of the interleaved arrays: stride 2
   for (int a = 0; a < 4; ++a) {
     if (!srcs[a]) continue;
     CU_TRY(s, cudaMemcpyAsync(d_val, srcs[a], m * sizeof(double), cudaMemcpyHostToDevice, s->stream));
     scatter_by_id_kernel<double><<<blocks_for(m, 256), 256, 0, s->stream>>>(
         (uint32_t)m, s->order_by_id, d_ids, s->slot_of_id, std::max<uint64_t>(s->max_id_plus1, 1), d_val, 1, dsts[a],
-        s->d_bad);
+        2, s->d_bad);
     s->launches += 1;
   }
   unsigned int bad = 0;
@@ -443,7 +433,7 @@ int rcs_set_preferred_velocity(rcs_sim* s, uint64_t m, const uint64_t* ids, cons
   if (!s || (m && !vxy)) return RCS_ERR_ARG;
   if (m == 0) return RCS_OK;
   CU_TRY(s, cudaSetDevice(s->device));
-  if (!s->cur.pvx) {
+  if (!s->cur.pv) {
     s->err = "no rcs_hl_host planner exists on this handle";
     return RCS_ERR_ARG;
   }
@@ -470,10 +460,12 @@ int rcs_set_preferred_velocity(rcs_sim* s, uint64_t m, const uint64_t* ids, cons
   CU_TRY(s, cudaMemsetAsync(s->d_bad, 0, sizeof(unsigned int), s->stream));
   const uint64_t L = std::max<uint64_t>(s->max_id_plus1, 1);
   scatter_by_id_kernel<double><<<blocks_for(m, 256), 256, 0, s->stream>>>((uint32_t)m, s->order_by_id, d_ids,
-                                                                          s->slot_of_id, L, d_val, 2, s->cur.pvx,
+                                                                          s->slot_of_id, L, d_val, 2,
+                                                                          reinterpret_cast<double*>(s->cur.pv), 2,
                                                                           s->d_bad);
   scatter_by_id_kernel<double><<<blocks_for(m, 256), 256, 0, s->stream>>>((uint32_t)m, s->order_by_id, d_ids,
-                                                                          s->slot_of_id, L, d_val + 1, 2, s->cur.pvy,
+                                                                          s->slot_of_id, L, d_val + 1, 2,
+                                                                          reinterpret_cast<double*>(s->cur.pv) + 1, 2,
                                                                           s->d_bad);
   s->launches += 2;
   CU_TRY(s, cudaGetLastError());
@@ -509,26 +501,19 @@ int rcs_read_agents(rcs_sim* s, uint32_t order, uint64_t cap, uint64_t* ids, dou
     if (rc) return rc;
     ord = s->order_by_id;
   }
-  if (!ord) {
-    // storage order: straight copies
-    if (ids) CU_TRY(s, cudaMemcpyAsync(ids, s->cur.id, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
-    if (x) CU_TRY(s, cudaMemcpyAsync(x, s->cur.x, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    if (y) CU_TRY(s, cudaMemcpyAsync(y, s->cur.y, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    if (vx) CU_TRY(s, cudaMemcpyAsync(vx, s->cur.vx, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    if (vy) CU_TRY(s, cudaMemcpyAsync(vy, s->cur.vy, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    if (next_waypoint)
-      CU_TRY(s, cudaMemcpyAsync(next_waypoint, s->cur.wp, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-  } else {
-    rc = ensure_stage(s, (uint64_t)n * 48 + 256);
-    if (rc) return rc;
-    uint64_t off = 0;
-    if (ids) { rc = read_array<uint64_t>(s, s->cur.id, ord, n, ids, off); off += (uint64_t)n * 8; if (rc) return rc; }
-    if (x) { rc = read_array<double>(s, s->cur.x, ord, n, x, off); off += (uint64_t)n * 8; if (rc) return rc; }
-    if (y) { rc = read_array<double>(s, s->cur.y, ord, n, y, off); off += (uint64_t)n * 8; if (rc) return rc; }
-    if (vx) { rc = read_array<double>(s, s->cur.vx, ord, n, vx, off); off += (uint64_t)n * 8; if (rc) return rc; }
-    if (vy) { rc = read_array<double>(s, s->cur.vy, ord, n, vy, off); off += (uint64_t)n * 8; if (rc) return rc; }
-    if (next_waypoint) { rc = read_array<uint32_t>(s, s->cur.wp, ord, n, next_waypoint, off); if (rc) return rc; }
-  }
+  // positions and velocities are stored as interleaved pairs: every requested component is gathered (in the
+  // requested order; identity for storage order) into a staging buffer and copied out from there
+  rc = ensure_stage(s, (uint64_t)n * 48 + 256);
+  if (rc) return rc;
+  const double* posd = reinterpret_cast<const double*>(s->cur.pos);
+  const double* veld = reinterpret_cast<const double*>(s->cur.vel);
+  uint64_t off = 0;
+  if (ids) { rc = read_array<uint64_t>(s, s->cur.id, 1, ord, n, ids, off); off += (uint64_t)n * 8; if (rc) return rc; }
+  if (x) { rc = read_array<double>(s, posd, 2, ord, n, x, off); off += (uint64_t)n * 8; if (rc) return rc; }
+  if (y) { rc = read_array<double>(s, posd + 1, 2, ord, n, y, off); off += (uint64_t)n * 8; if (rc) return rc; }
+  if (vx) { rc = read_array<double>(s, veld, 2, ord, n, vx, off); off += (uint64_t)n * 8; if (rc) return rc; }
+  if (vy) { rc = read_array<double>(s, veld + 1, 2, ord, n, vy, off); off += (uint64_t)n * 8; if (rc) return rc; }
+  if (next_waypoint) { rc = read_array<uint32_t>(s, s->cur.wp, 1, ord, n, next_waypoint, off); if (rc) return rc; }
   CU_TRY(s, cudaStreamSynchronize(s->stream));
   if (next_waypoint && s->any_route)  // the high half of the word is the route follower's cache entry
     for (uint32_t k = 0; k < n; ++k) next_waypoint[k] &= WP_MASK;
@@ -578,13 +563,15 @@ int rcs_read_agents_async(rcs_sim* s, uint32_t order, uint64_t cap, uint64_t* id
   }
   // the previous read's copies must have drained the staging buffer before it is overwritten (device-side wait)
   if (s->read_inflight) CU_TRY(s, cudaStreamWaitEvent(s->stream, s->ev_read_done, 0));
-  struct Item { const void* src; void* dst; };
-  const Item items[5] = {{s->cur.id, ids}, {s->cur.x, x}, {s->cur.y, y}, {s->cur.vx, vx}, {s->cur.vy, vy}};
+  struct Item { const void* src; int stride; void* dst; };
+  const double* posd = reinterpret_cast<const double*>(s->cur.pos);
+  const double* veld = reinterpret_cast<const double*>(s->cur.vel);
+  const Item items[5] = {{s->cur.id, 1, ids}, {posd, 2, x}, {posd + 1, 2, y}, {veld, 2, vx}, {veld + 1, 2, vy}};
   char* base = static_cast<char*>(s->stage2);
   for (int k = 0; k < 5; ++k) {
     if (!items[k].dst) continue;
     gather_kernel<unsigned long long><<<blocks_for(n, 256), 256, 0, s->stream>>>(
-        n, ord, static_cast<const unsigned long long*>(items[k].src),
+        n, ord, static_cast<const unsigned long long*>(items[k].src), items[k].stride,
         reinterpret_cast<unsigned long long*>(base + (uint64_t)k * n * 8));  // 8-byte elements, bit copies
     s->launches += 1;
   }

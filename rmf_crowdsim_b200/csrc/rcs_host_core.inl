@@ -44,20 +44,18 @@ static double radius_threshold(double R) {
 }
 
 static int alloc_agent_arrays(rcs_sim* s, AgentArrays& a, uint64_t cap) {
-  CU_TRY(s, dalloc(&a.x, cap));
-  CU_TRY(s, dalloc(&a.y, cap));
-  CU_TRY(s, dalloc(&a.vx, cap));
-  CU_TRY(s, dalloc(&a.vy, cap));
+  CU_TRY(s, dalloc(&a.pos, cap));
+  CU_TRY(s, dalloc(&a.vel, cap));
   CU_TRY(s, dalloc(&a.id, cap));
   CU_TRY(s, dalloc(&a.grp, cap));
   CU_TRY(s, dalloc(&a.wp, cap));
-  a.pvx = a.pvy = nullptr;
+  a.pv = nullptr;
   return RCS_OK;
 }
 
 static void free_agent_arrays(AgentArrays& a) {
-  cudaFree(a.x); cudaFree(a.y); cudaFree(a.vx); cudaFree(a.vy);
-  cudaFree(a.id); cudaFree(a.grp); cudaFree(a.wp); cudaFree(a.pvx); cudaFree(a.pvy);
+  cudaFree(a.pos); cudaFree(a.vel);
+  cudaFree(a.id); cudaFree(a.grp); cudaFree(a.wp); cudaFree(a.pv);
   a = AgentArrays{};
 }
 
@@ -152,15 +150,13 @@ static uint32_t find_or_add_group(rcs_sim* s, uint32_t hl, uint32_t lp, double e
 }
 
 static int ensure_pref_arrays(rcs_sim* s) {
-  if (s->cur.pvx) return RCS_OK;
+  if (s->cur.pv) return RCS_OK;
   CU_TRY(s, cudaStreamSynchronize(s->stream));
   const double nan = std::numeric_limits<double>::quiet_NaN();
   for (AgentArrays* a : {&s->cur, &s->srt}) {
-    CU_TRY(s, dalloc(&a->pvx, s->cap));
-    CU_TRY(s, dalloc(&a->pvy, s->cap));
-    fill_f64_kernel<<<blocks_for(s->cap, 256), 256, 0, s->stream>>>(s->cap, a->pvx, nan);
-    fill_f64_kernel<<<blocks_for(s->cap, 256), 256, 0, s->stream>>>(s->cap, a->pvy, nan);
-    s->launches += 2;
+    CU_TRY(s, dalloc(&a->pv, s->cap));
+    fill_f64_kernel<<<blocks_for(2 * s->cap, 256), 256, 0, s->stream>>>(2 * s->cap, reinterpret_cast<double*>(a->pv), nan);
+    s->launches += 1;
   }
   CU_TRY(s, cudaGetLastError());
   // pointer roles recorded for pending steps are stale now, but ensure_pref_arrays only runs right after a sync
@@ -188,8 +184,8 @@ static int upload_counts(rcs_sim* s) {
 static int bin_agents(rcs_sim* s, uint32_t n_ub, const uint32_t* first, uint32_t launch_n = 0) {
   if (!n_ub) return RCS_OK;
   if (!launch_n) launch_n = n_ub;  // threads to launch: fewer than n_ub when only the tail behind *first is binned
-  bin_count_kernel<<<blocks_for(launch_n, 256), 256, 0, s->stream>>>(s->grid, n_ub, first, s->cnt + CNT_TOT, s->cur.x,
-                                                                 s->cur.y, s->cur_has_dead ? s->keep : nullptr,
+  bin_count_kernel<<<blocks_for(launch_n, 256), 256, 0, s->stream>>>(s->grid, n_ub, first, s->cnt + CNT_TOT, s->cur.pos,
+                                                                 s->cur_has_dead ? s->keep : nullptr,
                                                                  s->cellid, s->cell_count, s->cell_lo, s->cell_hi,
                                                                  s->d_status);
   s->launches += 1;
@@ -218,7 +214,7 @@ static int sort_into_srt(rcs_sim* s, uint32_t n_ub) {
                                                                            s->big_list, 4096, s->d_status);
     sort_big_cells_kernel<<<148, 1024, 0, s->stream>>>(lo, hi, s->cell_start, s->cur.id, s->perm, s->slow_list,
                                                        s->big_list, 4096, s->d_status);
-    gather_sorted_kernel<<<blocks_for((n_ub + 1) / 2, 256), 256, 0, s->stream>>>(
+    gather_sorted_kernel<<<blocks_for(n_ub, 256), 256, 0, s->stream>>>(
         n_ub, s->perm, s->cur, s->srt, s->cellid, s->strip.enabled ? s->srt_cell : nullptr, n_sorted_ptr(s),
         s->grid, s->cell_start, s->d_groups, s->d_groups ? s->slices : nullptr, s->d_status);
     s->launches += 4;
@@ -455,10 +451,12 @@ static int build_slot_table(rcs_sim* s) {
   return RCS_OK;
 }
 
+// src: first element of the component to read; stride 2 for one component of a double2 array
 template <class T>
-static int read_array(rcs_sim* s, const T* src, const uint32_t* order, uint32_t n, T* host_out, uint64_t stage_off) {
+static int read_array(rcs_sim* s, const T* src, int stride, const uint32_t* order, uint32_t n, T* host_out,
+                      uint64_t stage_off) {
   T* st = reinterpret_cast<T*>(static_cast<char*>(s->stage) + stage_off);
-  gather_kernel<T><<<blocks_for(n, 256), 256, 0, s->stream>>>(n, order, src, st);
+  gather_kernel<T><<<blocks_for(n, 256), 256, 0, s->stream>>>(n, order, src, stride, st);
   s->launches += 1;
   CU_TRY(s, cudaMemcpyAsync(host_out, st, (uint64_t)n * sizeof(T), cudaMemcpyDeviceToHost, s->stream));
   return RCS_OK;

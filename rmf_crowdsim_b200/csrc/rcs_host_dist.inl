@@ -61,14 +61,11 @@ static int halo_alloc(rcs_sim* s, HaloMem& m, uint32_t cap) {
   HaloBuf& b = m.buf;
   b.count = reinterpret_cast<uint32_t*>(p);
   double* arr = reinterpret_cast<double*>(p + 64);
-  b.x = arr;
-  b.y = arr + (uint64_t)cap;
-  b.vx = arr + 2ull * cap;
-  b.vy = arr + 3ull * cap;
+  b.pos = reinterpret_cast<double2*>(arr);
+  b.vel = reinterpret_cast<double2*>(arr + 2ull * cap);
   b.id = reinterpret_cast<unsigned long long*>(arr + 4ull * cap);
   b.meta = reinterpret_cast<unsigned long long*>(arr + 5ull * cap);
-  b.pvx = arr + 6ull * cap;
-  b.pvy = arr + 7ull * cap;
+  b.pv = reinterpret_cast<double2*>(arr + 6ull * cap);
   b.cap = cap;
   return RCS_OK;
 }
@@ -128,7 +125,7 @@ static int strip_setup(rcs_sim* s, int rank, int world, uint64_t halo_capacity) 
     if (rc) return rc;
   }
   CU_TRY(s, dalloc(&s->srt_cell, s->cap + 16));
-  if (!s->cur.pvx) {
+  if (!s->cur.pv) {
     // ghosts carry the host-planner preferred velocity only when such a planner exists; the halo buffers
     // always have room for it
   }

@@ -49,7 +49,7 @@ int rcs_query_radius(rcs_sim* s, uint64_t nq, const double* qxy, const double* r
   CU_TRY(s, cudaMemcpyAsync(d_q, qxy, nq * 16, cudaMemcpyHostToDevice, s->stream));
   CU_TRY(s, cudaMemcpyAsync(d_r, radius, nq * 8, cudaMemcpyHostToDevice, s->stream));
   CU_TRY(s, cudaMemcpyAsync(d_t, thr.data(), nq * 8, cudaMemcpyHostToDevice, s->stream));
-  query_radius_kernel<<<blocks_for(nq, 128), 128, 0, s->stream>>>(s->grid, s->cell_start, s->srt.x, s->srt.y, s->srt.id,
+  query_radius_kernel<<<blocks_for(nq, 128), 128, 0, s->stream>>>(s->grid, s->cell_start, s->srt.pos, s->srt.id,
                                                                   (uint32_t)nq, d_q, d_r, d_t, d_c, nullptr, nullptr, 0);
   s->launches += 1;
   std::vector<uint32_t> counts(nq);
@@ -71,7 +71,7 @@ int rcs_query_radius(rcs_sim* s, uint64_t nq, const double* qxy, const double* r
   CU_TRY(s, cudaMalloc(reinterpret_cast<void**>(&d_off), (nq + 1) * 8));
   CU_TRY(s, cudaMalloc(reinterpret_cast<void**>(&d_ids), total * 8));
   cudaMemcpyAsync(d_off, offsets, (nq + 1) * 8, cudaMemcpyHostToDevice, s->stream);
-  query_radius_kernel<<<blocks_for(nq, 128), 128, 0, s->stream>>>(s->grid, s->cell_start, s->srt.x, s->srt.y, s->srt.id,
+  query_radius_kernel<<<blocks_for(nq, 128), 128, 0, s->stream>>>(s->grid, s->cell_start, s->srt.pos, s->srt.id,
                                                                   (uint32_t)nq, d_q, d_r, d_t, d_c, d_off, d_ids, 1);
   s->launches += 1;
   cudaMemcpyAsync(out_ids, d_ids, total * 8, cudaMemcpyDeviceToHost, s->stream);
@@ -122,7 +122,7 @@ int rcs_query_knn(rcs_sim* s, uint64_t nq, const double* qxy, uint64_t k, uint64
     cleanup();
     CU_TRY(s, e);
   }
-  knn_fill_kernel<<<blocks_for(nq, 128), 128, 0, s->stream>>>(s->grid, s->cell_start, s->srt.x, s->srt.y, (uint32_t)nq,
+  knn_fill_kernel<<<blocks_for(nq, 128), 128, 0, s->stream>>>(s->grid, s->cell_start, s->srt.pos, (uint32_t)nq,
                                                               d_q, k, d_o, d_slot, d_dist);
   knn_select_kernel<<<blocks_for(nq * 32, 128), 128, 0, s->stream>>>((uint32_t)nq, k, d_o, d_slot, d_dist, s->srt.id,
                                                                      d_out, d_cnt);

@@ -81,16 +81,13 @@ static StepArgs make_step_args(rcs_sim* s, const AgentArrays& in, const AgentArr
   a.cell_start = s->cell_start;
   a.groups = s->d_groups;
   a.dt = dt;
-  a.ox = out.x;
-  a.oy = out.y;
-  a.ovx = out.vx;
-  a.ovy = out.vy;
+  a.opos = out.pos;
+  a.ovel = out.vel;
   if (full_out) {
     a.oid = out.id;
     a.ogrp = out.grp;
     a.owp = out.wp;
-    a.opvx = in.pvx ? out.pvx : nullptr;
-    a.opvy = in.pvx ? out.pvy : nullptr;
+    a.opv = in.pv ? out.pv : nullptr;
   }
   a.status = s->d_status;
   a.collect_stats = 1;
@@ -154,7 +151,7 @@ static int step_phase_a(rcs_sim* s, double dt) {
     const uint32_t n_before = s->n_ub;
     if (n_before)
       ss_probe_kernel<<<blocks_for(n_before, 256), 256, 0, s->stream>>>(
-          s->grid, s->sgrid, s->d_sources, radius_threshold(0.4), n_before, s->cnt + CNT_CUR, s->cur.x, s->cur.y,
+          s->grid, s->sgrid, s->d_sources, radius_threshold(0.4), n_before, s->cnt + CNT_CUR, s->cur.pos,
           s->cur_has_dead ? s->keep : nullptr, s->d_blocked, s->d_status);
     ss_spawn_kernel<<<1, SCAN_THREADS, 0, s->stream>>>(s->grid, s->d_sources, s->d_groups, (uint32_t)s->sources.size(), dt,
                                                        s->d_blocked, s->cur, s->keep, (uint32_t)s->cap, s->cnt, s->d_next_id,
@@ -272,10 +269,8 @@ static int step_phase_b(rcs_sim* s, double dt, uint32_t flags) {
     launch_step_kernel(s, a, n_ub, false);
     p.snapshot_in_srt = false;
     if (!no_commit) {
-      std::swap(s->cur.x, s->srt.x);
-      std::swap(s->cur.y, s->srt.y);
-      std::swap(s->cur.vx, s->srt.vx);
-      std::swap(s->cur.vy, s->srt.vy);
+      std::swap(s->cur.pos, s->srt.pos);
+      std::swap(s->cur.vel, s->srt.vel);
     }
   }
   end_step_kernel<<<1, 1, 0, s->stream>>>(s->d_status, no_commit ? 0 : 1, s->d_steps_done,

@@ -56,11 +56,13 @@ struct StripDev {
   uint32_t pad_;
 };
 
+// Structure of arrays with the two f64 components of a vector interleaved, so that every position / velocity
+// moves with one 16-byte access.
 struct AgentArrays {
-  double *x, *y, *vx, *vy;
+  double2 *pos, *vel;
   uint64_t* id;
   uint32_t *grp, *wp;
-  double *pvx, *pvy;  // host-planner preferred velocities; NaN = None.  nullptr if no host planner exists
+  double2* pv;  // host-planner preferred velocities; NaN in .x = None.  nullptr if no host planner exists
 };
 
 constexpr int SCAN_THREADS = 256;
@@ -76,8 +78,8 @@ constexpr uint32_t CELL_DEAD = 0xffffffffu;
 // at a sink, migrated to another strip, ghosts of the previous step) are dropped here: the counting sort of the
 // next step is the stream compaction.
 __global__ void bin_count_kernel(GridDev g, uint32_t n_ub, const uint32_t* __restrict__ first,
-                                 const uint32_t* __restrict__ last, const double* __restrict__ x,
-                                 const double* __restrict__ y, const uint32_t* __restrict__ keep,
+                                 const uint32_t* __restrict__ last, const double2* __restrict__ pos,
+                                 const uint32_t* __restrict__ keep,
                                  uint32_t* __restrict__ cellid, uint32_t* __restrict__ cell_count, uint64_t cell_lo,
                                  uint64_t cell_hi, DevStatus* status) {
   if (status->failed) return;
@@ -88,7 +90,8 @@ __global__ void bin_count_kernel(GridDev g, uint32_t n_ub, const uint32_t* __res
     return;
   }
   uint64_t idx;
-  if (location_to_index(g, x[i], y[i], idx)) {
+  const double2 p = pos[i];
+  if (location_to_index(g, p.x, p.y, idx)) {
     if (idx < cell_lo || idx >= cell_hi) {
       // strips index only the cells of their own columns and halo; an agent elsewhere (possible only through the
       // row aliasing of location_hash_2d.rs:59 far above the grid) cannot be handled by this rank
@@ -366,9 +369,8 @@ __device__ __forceinline__ uint4 query_slices(const GridDev& g, const uint32_t* 
   return sl;
 }
 
-// Two sorted slots per thread.  The arrays being gathered are last step's sorted output and agents rarely change
-// cell, so perm[k], perm[k+1] are usually an aligned consecutive pair: then every array moves with 16-byte
-// accesses (8-byte for the two 4-byte arrays); otherwise element by element.
+// One sorted slot per thread; positions and velocities move as 16-byte elements.  The arrays being gathered are
+// last step's sorted output and agents rarely change cell, so perm is close to the identity and the reads coalesce.
 __global__ void gather_sorted_kernel(uint32_t n, const uint32_t* __restrict__ perm, AgentArrays cur,
                                      AgentArrays srt, const uint32_t* __restrict__ cellid,
                                      uint32_t* __restrict__ srt_cell, const uint32_t* __restrict__ n_sorted,
@@ -376,59 +378,19 @@ __global__ void gather_sorted_kernel(uint32_t n, const uint32_t* __restrict__ pe
                                      const GroupDev* __restrict__ groups, uint4* __restrict__ slices,
                                      const DevStatus* status) {
   if (status->failed) return;
-  const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) * 2u;
-  const uint32_t lim = min(n, *n_sorted);
-  if (k >= lim) return;
-  const bool two = k + 1u < lim;
-  const uint32_t i0 = perm[k];
-  const uint32_t i1 = two ? perm[k + 1u] : 0u;
-  double px[2], py[2];
-  uint32_t grp[2];
-  if (two && i1 == i0 + 1u && (i0 & 1u) == 0u) {
-    const double2 vx2 = *reinterpret_cast<const double2*>(cur.x + i0);
-    const double2 vy2 = *reinterpret_cast<const double2*>(cur.y + i0);
-    const uint2 g2 = *reinterpret_cast<const uint2*>(cur.grp + i0);
-    *reinterpret_cast<double2*>(srt.x + k) = vx2;
-    *reinterpret_cast<double2*>(srt.y + k) = vy2;
-    *reinterpret_cast<double2*>(srt.vx + k) = *reinterpret_cast<const double2*>(cur.vx + i0);
-    *reinterpret_cast<double2*>(srt.vy + k) = *reinterpret_cast<const double2*>(cur.vy + i0);
-    *reinterpret_cast<ulonglong2*>(srt.id + k) = *reinterpret_cast<const ulonglong2*>(cur.id + i0);
-    *reinterpret_cast<uint2*>(srt.grp + k) = g2;
-    *reinterpret_cast<uint2*>(srt.wp + k) = *reinterpret_cast<const uint2*>(cur.wp + i0);
-    if (cur.pvx) {
-      *reinterpret_cast<double2*>(srt.pvx + k) = *reinterpret_cast<const double2*>(cur.pvx + i0);
-      *reinterpret_cast<double2*>(srt.pvy + k) = *reinterpret_cast<const double2*>(cur.pvy + i0);
-    }
-    if (srt_cell) *reinterpret_cast<uint2*>(srt_cell + k) = *reinterpret_cast<const uint2*>(cellid + i0);
-    px[0] = vx2.x; px[1] = vx2.y;
-    py[0] = vy2.x; py[1] = vy2.y;
-    grp[0] = g2.x; grp[1] = g2.y;
-  } else {
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      if (e == 1 && !two) break;
-      const uint32_t i = e ? i1 : i0;
-      px[e] = cur.x[i];
-      py[e] = cur.y[i];
-      grp[e] = cur.grp[i];
-      if (srt_cell) srt_cell[k + e] = cellid[i];
-      srt.x[k + e] = px[e];
-      srt.y[k + e] = py[e];
-      srt.vx[k + e] = cur.vx[i];
-      srt.vy[k + e] = cur.vy[i];
-      srt.id[k + e] = cur.id[i];
-      srt.grp[k + e] = grp[e];
-      srt.wp[k + e] = cur.wp[i];
-      if (cur.pvx) {
-        srt.pvx[k + e] = cur.pvx[i];
-        srt.pvy[k + e] = cur.pvy[i];
-      }
-    }
-  }
-  if (slices) {
-    slices[k] = query_slices(g, cell_start, groups[grp[0]], px[0], py[0]);
-    if (two) slices[k + 1u] = query_slices(g, cell_start, groups[grp[1]], px[1], py[1]);
-  }
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n || k >= *n_sorted) return;
+  const uint32_t i = perm[k];
+  const double2 p = cur.pos[i];
+  const uint32_t grp = cur.grp[i];
+  if (srt_cell) srt_cell[k] = cellid[i];
+  srt.pos[k] = p;
+  srt.vel[k] = cur.vel[i];
+  srt.id[k] = cur.id[i];
+  srt.grp[k] = grp;
+  srt.wp[k] = cur.wp[i];
+  if (cur.pv) srt.pv[k] = cur.pv[i];
+  if (slices) slices[k] = query_slices(g, cell_start, groups[grp], p.x, p.y);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -442,10 +404,10 @@ struct StepArgs {
   const uint32_t* cell_start; // len + 1
   const GroupDev* groups;
   double dt;                  // Duration::as_secs_f64 (lib.rs:295)
-  double *ox, *oy, *ovx, *ovy;  // new state, same order
+  double2 *opos, *ovel;        // new state, same order
   uint64_t* oid;              // id / group / waypoint / host preferred velocity of the new state
   uint32_t *ogrp, *owp;       //   (all nullptr on the streaming path, which updates x,y,vx,vy in place)
-  double *opvx, *opvy;
+  double2* opv;
   double *t_i, *fx, *fy;      // optional trace outputs (nullptr when tracing is off)
   uint32_t* nb_count;         // optional: neighbour count per agent (trace)
   uint64_t* tr_id;            // optional: id of the agent in each trace slot
@@ -497,7 +459,7 @@ struct Self {
 // in canonical order.  Returns the number of candidates distance-tested.
 template <class F>
 __device__ __forceinline__ uint32_t for_each_neighbour(const GridDev& g, const uint32_t* __restrict__ cell_start,
-                                                       const double* __restrict__ xs, const double* __restrict__ ys,
+                                                       const double2* __restrict__ pos,
                                                        const uint64_t* __restrict__ ids, double px, double py,
                                                        uint64_t self_id, double radius, double thr2, F&& f) {
   int64_t left, right, bottom, top;
@@ -511,8 +473,9 @@ __device__ __forceinline__ uint32_t for_each_neighbour(const GridDev& g, const u
     uint32_t s = cell_start[c_lo], e = cell_start[c_hi + 1];
     cand += e - s;
     for (uint32_t j = s; j < e; ++j) {
-      double dx = xs[j] - px;
-      double dy = ys[j] - py;
+      const double2 q = pos[j];
+      double dx = q.x - px;
+      double dy = q.y - py;
       double d2 = dx * dx + dy * dy;
       if (d2 < thr2) {
         if (ids[j] != self_id) f(j, dx, dy, d2);
@@ -529,31 +492,31 @@ __device__ __forceinline__ uint32_t for_each_neighbour(const GridDev& g, const u
 __device__ __noinline__ void zanlungo_sequential(const StepArgs& a, uint32_t i, const Self& me, const GroupDev& g,
                                                  double& t_i, double& fx, double& fy, uint32_t& nbc,
                                                  uint32_t& cand) {
-  const double* __restrict__ xs = a.in.x;
-  const double* __restrict__ ys = a.in.y;
-  const double* __restrict__ vxs = a.in.vx;
-  const double* __restrict__ vys = a.in.vy;
+  const double2* __restrict__ pos = a.in.pos;
+  const double2* __restrict__ vel = a.in.vel;
   const uint64_t* __restrict__ ids = a.in.id;
   const double rr = g.rr;
   t_i = RCS_INF;
   fx = 0.0;
   fy = 0.0;
   // Zanlungo::compute_tti, zanlungo.rs:76-91
-  cand = for_each_neighbour(a.grid, a.cell_start, xs, ys, ids, me.px, me.py, me.id, g.eyesight, g.thr2,
+  cand = for_each_neighbour(a.grid, a.cell_start, pos, ids, me.px, me.py, me.id, g.eyesight, g.thr2,
                             [&](uint32_t j, double dx, double dy, double d2) {
                               nbc++;
-                              double col_time = time_to_collision(vxs[j] - me.vx, vys[j] - me.vy, dx, dy, d2, rr);
+                              const double2 nv = vel[j];
+                              double col_time = time_to_collision(nv.x - me.vx, nv.y - me.vy, dx, dy, d2, rr);
                               if (col_time < t_i) t_i = col_time;
                             });
   // zanlungo.rs:210-215
   if (t_i != RCS_INF) {
     const OwnerPre pre = owner_precompute(me.px, me.py, me.vx, me.vy, me.pfx, me.pfy, t_i, g);
     const double ti = t_i;
-    for_each_neighbour(a.grid, a.cell_start, xs, ys, ids, me.px, me.py, me.id, g.eyesight, g.thr2,
+    for_each_neighbour(a.grid, a.cell_start, pos, ids, me.px, me.py, me.id, g.eyesight, g.thr2,
                        [&](uint32_t j, double, double, double) {
                          double qx, qy;
-                         if (pair_force_dispatch(pre, me.px, me.py, me.vx, me.vy, me.pfx, me.pfy, me.id, xs[j], ys[j],
-                                                 vxs[j], vys[j], ids[j], ti, g, qx, qy)) {
+                         const double2 np = pos[j], nv = vel[j];
+                         if (pair_force_dispatch(pre, me.px, me.py, me.vx, me.vy, me.pfx, me.pfy, me.id, np.x, np.y,
+                                                 nv.x, nv.y, ids[j], ti, g, qx, qy)) {
                            fx = fx + qx;
                            fy = fy + qy;
                          }
@@ -609,7 +572,8 @@ __device__ __forceinline__ void high_level_velocity(const StepArgs& a, uint32_t 
       me.rwp = rw;
     } break;
     case HL_HOST: {
-      double hx = a.in.pvx[i], hy = a.in.pvy[i];
+      const double2 hv = a.in.pv[i];
+      double hx = hv.x, hy = hv.y;
       if (hx == hx) {  // NaN in x encodes None
         velx = hx;
         vely = hy;
@@ -629,10 +593,8 @@ __device__ __forceinline__ void integrate_and_store(const StepArgs& a, uint32_t 
                                                     double vely, double t_i, double fx, double fy, uint32_t nbc) {
   const double nx = me.px + velx * a.dt;
   const double ny = me.py + vely * a.dt;
-  a.ox[i] = nx;
-  a.oy[i] = ny;
-  a.ovx[i] = velx;
-  a.ovy[i] = vely;
+  a.opos[i] = make_double2(nx, ny);
+  a.ovel[i] = make_double2(velx, vely);
   const bool own = role == ROLE_OWN;
   if (a.t_i) {
     a.t_i[i] = t_i;
@@ -691,10 +653,7 @@ __device__ __forceinline__ void integrate_and_store(const StepArgs& a, uint32_t 
   a.oid[i] = me.id;
   a.ogrp[i] = grp;
   a.owp[i] = wp | (rwp << WP_ROUTE_SHIFT);
-  if (a.opvx) {
-    a.opvx[i] = a.in.pvx[i];
-    a.opvy[i] = a.in.pvy[i];
-  }
+  if (a.opv) a.opv[i] = a.in.pv[i];
   if (a.strip.enabled) {
     // The agent stays with the rank that owns its NEW column.  Every agent that leaves a strip must have
     // been in the neighbour's ring (old column within h of the boundary) and must land inside the
@@ -739,10 +698,11 @@ __device__ __forceinline__ void step_one_agent(const StepArgs& a, uint32_t i, ui
   }
   const GroupDev& g = a.groups[a.in.grp[i]];
   Self me;
-  me.px = a.in.x[i];
-  me.py = a.in.y[i];
-  me.vx = a.in.vx[i];
-  me.vy = a.in.vy[i];
+  const double2 p0 = a.in.pos[i], v0 = a.in.vel[i];
+  me.px = p0.x;
+  me.py = p0.y;
+  me.vx = v0.x;
+  me.vy = v0.y;
   me.id = a.in.id[i];
   me.rwp = 0u;
   double velx, vely;
@@ -814,45 +774,39 @@ __device__ __forceinline__ void stream_one(const StepArgs& a, const GroupDev& g,
 __global__ void __launch_bounds__(256) step_stream_kernel(StepArgs a) {
   const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) * 2u;
   if (i >= a.n) return;
-  const bool pair = i + 1u < a.n;  // every array holds at least a.n entries (a.n is even-padded by cudaMalloc)
-  double2 p_x, p_y, h_x = make_double2(0.0, 0.0), h_y = make_double2(0.0, 0.0);
+  const bool pair = i + 1u < a.n;  // every array holds at least a.n entries
+  // two agents per thread: 32 bytes of positions, 16 of ids, 8 of groups per access
+  double4 pp;
   ulonglong2 p_id;
   uint2 p_g;
+  double4 hh = make_double4(0.0, 0.0, 0.0, 0.0);
   if (pair) {
-    p_x = *reinterpret_cast<const double2*>(a.in.x + i);
-    p_y = *reinterpret_cast<const double2*>(a.in.y + i);
+    pp = *reinterpret_cast<const double4*>(a.in.pos + i);
     p_id = *reinterpret_cast<const ulonglong2*>(a.in.id + i);
     p_g = *reinterpret_cast<const uint2*>(a.in.grp + i);
-    if (a.in.pvx) {
-      h_x = *reinterpret_cast<const double2*>(a.in.pvx + i);
-      h_y = *reinterpret_cast<const double2*>(a.in.pvy + i);
-    }
+    if (a.in.pv) hh = *reinterpret_cast<const double4*>(a.in.pv + i);
   } else {
-    p_x = make_double2(a.in.x[i], 0.0);
-    p_y = make_double2(a.in.y[i], 0.0);
+    const double2 p = a.in.pos[i];
+    pp = make_double4(p.x, p.y, 0.0, 0.0);
     p_id = make_ulonglong2(a.in.id[i], 0ull);
     p_g = make_uint2(a.in.grp[i], 0u);
-    if (a.in.pvx) {
-      h_x.x = a.in.pvx[i];
-      h_y.x = a.in.pvy[i];
+    if (a.in.pv) {
+      const double2 h = a.in.pv[i];
+      hh = make_double4(h.x, h.y, 0.0, 0.0);
     }
   }
   if (a.status->failed) return;
   const uint32_t n_live = *a.n_sorted;
   if (i >= n_live) return;
-  double2 o_x = p_x, o_y = p_y, o_vx = make_double2(0.0, 0.0), o_vy = make_double2(0.0, 0.0);
-  stream_one(a, a.groups[p_g.x], p_x.x, p_y.x, p_id.x, h_x.x, h_y.x, o_x.x, o_y.x, o_vx.x, o_vy.x);
+  double4 op = pp, ov = make_double4(0.0, 0.0, 0.0, 0.0);
+  stream_one(a, a.groups[p_g.x], pp.x, pp.y, p_id.x, hh.x, hh.y, op.x, op.y, ov.x, ov.y);
   if (pair && i + 1u < n_live) {
-    stream_one(a, a.groups[p_g.y], p_x.y, p_y.y, p_id.y, h_x.y, h_y.y, o_x.y, o_y.y, o_vx.y, o_vy.y);
-    *reinterpret_cast<double2*>(a.ox + i) = o_x;
-    *reinterpret_cast<double2*>(a.oy + i) = o_y;
-    *reinterpret_cast<double2*>(a.ovx + i) = o_vx;
-    *reinterpret_cast<double2*>(a.ovy + i) = o_vy;
+    stream_one(a, a.groups[p_g.y], pp.z, pp.w, p_id.y, hh.z, hh.w, op.z, op.w, ov.z, ov.w);
+    *reinterpret_cast<double4*>(a.opos + i) = op;
+    *reinterpret_cast<double4*>(a.ovel + i) = ov;
   } else {
-    a.ox[i] = o_x.x;
-    a.oy[i] = o_y.x;
-    a.ovx[i] = o_vx.x;
-    a.ovy[i] = o_vy.x;
+    a.opos[i] = make_double2(op.x, op.y);
+    a.ovel[i] = make_double2(ov.x, ov.y);
   }
 }
 
@@ -876,14 +830,15 @@ __global__ void trace_neighbours_kernel(StepArgs a, const uint32_t* __restrict__
   const GroupDev& g = a.groups[a.in.grp[i]];
   if (g.lp_kind != LP_ZANLUNGO) return;
   uint32_t o = nb_offsets[i];
-  for_each_neighbour(a.grid, a.cell_start, a.in.x, a.in.y, a.in.id, a.in.x[i], a.in.y[i], a.in.id[i], g.eyesight,
+  const double2 p0 = a.in.pos[i];
+  for_each_neighbour(a.grid, a.cell_start, a.in.pos, a.in.id, p0.x, p0.y, a.in.id[i], g.eyesight,
                      g.thr2, [&](uint32_t j, double, double, double) { nb_ids[o++] = a.in.id[j]; });
 }
 
 // SpatialIndex::get_neighbours_in_radius for arbitrary query points (location_hash_2d.rs:240-258).
 // mode 0: count into counts[q]; mode 1: write ids at offsets[q].  No self filter.
-__global__ void query_radius_kernel(GridDev g, const uint32_t* __restrict__ cell_start, const double* __restrict__ xs,
-                                    const double* __restrict__ ys, const uint64_t* __restrict__ ids, uint32_t nq,
+__global__ void query_radius_kernel(GridDev g, const uint32_t* __restrict__ cell_start,
+                                    const double2* __restrict__ pos, const uint64_t* __restrict__ ids, uint32_t nq,
                                     const double* __restrict__ qxy, const double* __restrict__ radius,
                                     const double* __restrict__ thr2, uint32_t* __restrict__ counts,
                                     const uint64_t* __restrict__ offsets, uint64_t* __restrict__ out_ids, int mode) {
@@ -893,7 +848,7 @@ __global__ void query_radius_kernel(GridDev g, const uint32_t* __restrict__ cell
   uint32_t cnt = 0;
   uint64_t o = mode ? offsets[q] : 0;
   // ids are < 2^63 in practice; ~0 never matches an agent so the self filter is a no-op here
-  for_each_neighbour(g, cell_start, xs, ys, ids, px, py, ~0ull, radius[q], thr2[q],
+  for_each_neighbour(g, cell_start, pos, ids, px, py, ~0ull, radius[q], thr2[q],
                      [&](uint32_t j, double, double, double) {
                        if (mode) out_ids[o++] = ids[j];
                        cnt++;
@@ -953,8 +908,8 @@ __global__ void knn_count_kernel(GridDev g, const uint32_t* __restrict__ cell_st
 }
 
 // pass 1: candidate slots and distances in visiting order (ascending id inside a cell)
-__global__ void knn_fill_kernel(GridDev g, const uint32_t* __restrict__ cell_start, const double* __restrict__ xs,
-                                const double* __restrict__ ys, uint32_t nq, const double* __restrict__ qxy, uint64_t k,
+__global__ void knn_fill_kernel(GridDev g, const uint32_t* __restrict__ cell_start,
+                                const double2* __restrict__ pos, uint32_t nq, const double* __restrict__ qxy, uint64_t k,
                                 const uint32_t* __restrict__ offsets, uint32_t* __restrict__ cand_slot,
                                 double* __restrict__ cand_dist) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -964,7 +919,8 @@ __global__ void knn_fill_kernel(GridDev g, const uint32_t* __restrict__ cell_sta
   knn_walk(g, px, py, k, [&](uint64_t c) {
     const uint32_t s = cell_start[c], e = cell_start[c + 1];
     for (uint32_t j = s; j < e; ++j) {
-      const double dx = xs[j] - px, dy = ys[j] - py;
+      const double2 c = pos[j];
+      const double dx = c.x - px, dy = c.y - py;
       cand_slot[o] = j;
       cand_dist[o] = sqrt(dx * dx + dy * dy);  // (a_pos - position).norm(), :227
       ++o;
@@ -1054,20 +1010,20 @@ __global__ void order_by_id_kernel(uint64_t table_len, const uint32_t* __restric
   if (s != 0xffffffffu) order_by_id[rank[v]] = s;
 }
 
-// out[k] = src[order[k]] (order == nullptr: identity)
+// out[k] = src[order[k] * stride] (order == nullptr: identity); stride 2 picks one component of a double2 array
 template <class T>
-__global__ void gather_kernel(uint32_t n, const uint32_t* __restrict__ order, const T* __restrict__ src,
+__global__ void gather_kernel(uint32_t n, const uint32_t* __restrict__ order, const T* __restrict__ src, int stride,
                               T* __restrict__ out) {
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  out[k] = src[order ? order[k] : k];
+  out[k] = src[(size_t)(order ? order[k] : k) * stride];
 }
 
 // dst[slot(k)] = src[k] where slot(k) = order[k] (ascending-id addressing) or slot_of_id[ids[k]]
 template <class T>
 __global__ void scatter_by_id_kernel(uint32_t n, const uint32_t* __restrict__ order, const uint64_t* __restrict__ ids,
                                      const uint32_t* __restrict__ slot_of_id, uint64_t table_len,
-                                     const T* __restrict__ src, int src_stride, T* __restrict__ dst,
+                                     const T* __restrict__ src, int src_stride, T* __restrict__ dst, int dst_stride,
                                      unsigned int* __restrict__ bad) {
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
@@ -1082,7 +1038,7 @@ __global__ void scatter_by_id_kernel(uint32_t n, const uint32_t* __restrict__ or
   } else {
     s = order[k];
   }
-  dst[s] = src[(size_t)k * src_stride];
+  dst[(size_t)s * dst_stride] = src[(size_t)k * src_stride];
 }
 
 // RMFPlanner::set_target for agents addressed by id: (route, 0) into the agent_cache (rmf/mod.rs:217-237)
@@ -1170,17 +1126,12 @@ __global__ void compact_keep_kernel(uint32_t n_ub, const uint32_t* __restrict__ 
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_ub || i >= *n_ptr || !keep[i]) return;
   uint32_t k = pos[i];
-  out.x[k] = in.x[i];
-  out.y[k] = in.y[i];
-  out.vx[k] = in.vx[i];
-  out.vy[k] = in.vy[i];
+  out.pos[k] = in.pos[i];
+  out.vel[k] = in.vel[i];
   out.id[k] = in.id[i];
   out.grp[k] = in.grp[i];
   out.wp[k] = in.wp[i];
-  if (in.pvx) {
-    out.pvx[k] = in.pvx[i];
-    out.pvy[k] = in.pvy[i];
-  }
+  if (in.pv) out.pv[k] = in.pv[i];
 }
 
 // keep flags beyond the live count must be 0 before the scan
@@ -1208,14 +1159,14 @@ struct SourceGridDev {
 };
 
 __global__ void ss_probe_kernel(GridDev g, SourceGridDev sg, const SourceSinkDev* __restrict__ ss, double thr2_probe,
-                                uint32_t n_ub, const uint32_t* __restrict__ n_ptr, const double* __restrict__ x,
-                                const double* __restrict__ y, const uint32_t* __restrict__ keep,
+                                uint32_t n_ub, const uint32_t* __restrict__ n_ptr,
+                                const double2* __restrict__ pos, const uint32_t* __restrict__ keep,
                                 uint32_t* __restrict__ blocked, const DevStatus* status) {
   if (status->failed) return;
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_ub || i >= *n_ptr) return;
   if (keep && !keep[i]) return;  // removed at the end of the previous step (lib.rs:378-380)
-  const double px = x[i], py = y[i];
+  const double px = pos[i].x, py = pos[i].y;
   // conservative range of lookup cells around the agent (0.4 m radius + slack)
   const double fx0 = floor((px - 0.45 - sg.x0) / sg.cell), fx1 = floor((px + 0.45 - sg.x0) / sg.cell);
   const double fy0 = floor((py - 0.45 - sg.y0) / sg.cell), fy1 = floor((py + 0.45 - sg.y0) / sg.cell);
@@ -1277,20 +1228,17 @@ __global__ void ss_spawn_kernel(GridDev g, const SourceSinkDev* __restrict__ ss,
       const uint32_t slot = n0 + off + rank;
       if (slot < cap) {
         const SourceSinkDev& s = ss[k];
-        cur.x[slot] = s.sx;
-        cur.y[slot] = s.sy;
-        cur.vx[slot] = 0.0;
-        cur.vy[slot] = 0.0;
+        cur.pos[slot] = make_double2(s.sx, s.sy);
+        cur.vel[slot] = make_double2(0.0, 0.0);
         cur.id[slot] = id0 + off + rank;
         cur.grp[slot] = s.grp;
         // set_target(agent, waypoints[0], ..) right after the spawn (lib.rs:242-249): a route follower starts at
         // the head of its route
         cur.wp[slot] = groups[s.grp].hl_kind == HL_ROUTE ? (1u << WP_ROUTE_SHIFT) : 0u;
         keep[slot] = 1u;
-        if (cur.pvx) {
-          cur.pvx[slot] = __longlong_as_double(0x7ff8000000000000LL);
-          cur.pvy[slot] = __longlong_as_double(0x7ff8000000000000LL);
-        }
+        if (cur.pv)
+          cur.pv[slot] = make_double2(__longlong_as_double(0x7ff8000000000000LL),
+                                      __longlong_as_double(0x7ff8000000000000LL));
         const uint32_t e = ev0 + off + rank;
         if (e < ev_cap) {
           ev_id[e] = id0 + off + rank;
@@ -1318,15 +1266,15 @@ __global__ void ss_spawn_kernel(GridDev g, const SourceSinkDev* __restrict__ ss,
 }
 
 // ---------------------------------------------------------------------------------------------
-// Strips: halo pack / unpack.  A halo buffer is [count u32, pad][x][y][vx][vy][id][meta][pvx][pvy],
+// Strips: halo pack / unpack.  A halo buffer is [count u32, pad][pos][vel][id][meta][pv],
 // each array `cap` entries.  Packed order is arbitrary (atomic append); the receiver re-sorts.
 // ---------------------------------------------------------------------------------------------
 struct HaloBuf {
   uint32_t* count;
-  double *x, *y, *vx, *vy;
+  double2 *pos, *vel;
   unsigned long long* id;
   unsigned long long* meta;  // grp | wp << 32
-  double *pvx, *pvy;
+  double2* pv;
   uint32_t cap;
 };
 
@@ -1348,16 +1296,11 @@ __global__ void halo_pack_kernel(uint32_t n_ub, const uint32_t* __restrict__ n_p
       atomicAdd(&status->capacity_err, 1u);
       continue;
     }
-    b.x[k] = cur.x[i];
-    b.y[k] = cur.y[i];
-    b.vx[k] = cur.vx[i];
-    b.vy[k] = cur.vy[i];
+    b.pos[k] = cur.pos[i];
+    b.vel[k] = cur.vel[i];
     b.id[k] = cur.id[i];
     b.meta[k] = (unsigned long long)cur.grp[i] | ((unsigned long long)cur.wp[i] << 32);
-    if (cur.pvx) {
-      b.pvx[k] = cur.pvx[i];
-      b.pvy[k] = cur.pvy[i];
-    }
+    if (cur.pv) b.pv[k] = cur.pv[i];
   }
 }
 
@@ -1396,18 +1339,13 @@ __global__ void halo_unpack_kernel(AgentArrays cur, uint32_t* __restrict__ keep,
   const uint32_t e = k < nl ? k : k - nl;
   const uint32_t slot = n0 + k;
   if (slot >= cap) return;
-  cur.x[slot] = b.x[e];
-  cur.y[slot] = b.y[e];
-  cur.vx[slot] = b.vx[e];
-  cur.vy[slot] = b.vy[e];
+  cur.pos[slot] = b.pos[e];
+  cur.vel[slot] = b.vel[e];
   cur.id[slot] = b.id[e];
   cur.grp[slot] = (uint32_t)(b.meta[e] & 0xffffffffull);
   cur.wp[slot] = (uint32_t)(b.meta[e] >> 32);
   keep[slot] = 1u;
-  if (cur.pvx) {
-    cur.pvx[slot] = b.pvx[e];
-    cur.pvy[slot] = b.pvy[e];
-  }
+  if (cur.pv) cur.pv[slot] = b.pv[e];
 }
 
 // FP64 pipe peak: independent DFMA / DADD chains.

@@ -58,10 +58,8 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 6) step_warp_kernel(StepArgs a)
   const unsigned FULL = 0xffffffffu;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 
-  const double* __restrict__ xs = a.in.x;
-  const double* __restrict__ ys = a.in.y;
-  const double* __restrict__ vxs = a.in.vx;
-  const double* __restrict__ vys = a.in.vy;
+  const double2* __restrict__ pos = a.in.pos;
+  const double2* __restrict__ vel = a.in.vel;
   const uint64_t* __restrict__ ids = a.in.id;
 
   // This warp's own rows go out first, before the status words are even looked at: every array holds at least
@@ -74,10 +72,11 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 6) step_warp_kernel(StepArgs a)
   uint4 sl = make_uint4(0u, 0u, 0u, 0u);
   const bool inb = i < a.n;
   if (inb) {
-    me.px = xs[i];
-    me.py = ys[i];
-    me.vx = vxs[i];
-    me.vy = vys[i];
+    const double2 p0 = pos[i], v0 = vel[i];
+    me.px = p0.x;
+    me.py = p0.y;
+    me.vx = v0.x;
+    me.vy = v0.y;
     me.id = ids[i];
     grp = a.in.grp[i];
     wp_in = a.in.wp[i];
@@ -142,8 +141,9 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 6) step_warp_kernel(StepArgs a)
     _Pragma("unroll 4")                                                \
     for (uint32_t t = 0; t < (MX); ++t) {                              \
       const uint32_t j = (t < (L)) ? (S) + t : iself;                  \
-      const double dx = xs[j] - me.px;                                 \
-      const double dy = ys[j] - me.py;                                 \
+      const double2 c = pos[j];                                        \
+      const double dx = c.x - me.px;                                   \
+      const double dy = c.y - me.py;                                   \
       const double d2 = dx * dx + dy * dy;                             \
       (M) |= ((d2 < thr2) && (j != i)) ? (1u << t) : 0u;               \
     }
@@ -174,10 +174,11 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 6) step_warp_kernel(StepArgs a)
         for (uint32_t e = lane; e < cnt; e += 32) {
           const uint32_t o = w.lo[e];
           const uint32_t j = w.lj[e];
-          const double dx = xs[j] - w.px[o];
-          const double dy = ys[j] - w.py[o];
+          const double2 c = pos[j], cv = vel[j];
+          const double dx = c.x - w.px[o];
+          const double dy = c.y - w.py[o];
           const double d2 = dx * dx + dy * dy;
-          const double ct = time_to_collision(vxs[j] - w.vx[o], vys[j] - w.vy[o], dx, dy, d2, w.rr[o]);
+          const double ct = time_to_collision(cv.x - w.vx[o], cv.y - w.vy[o], dx, dy, d2, w.rr[o]);
           if (ct < RCS_INF) atomicMin(&w.tbits[o], (unsigned long long)__double_as_longlong(ct));
         }
         __syncwarp();
@@ -210,10 +211,11 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 6) step_warp_kernel(StepArgs a)
         y0 |= (kk == 0u) ? bit : 0u;
         y1 |= (kk == 1u) ? bit : 0u;
         y2 |= (kk == 2u) ? bit : 0u;
-        const double dx = xs[j] - me.px;
-        const double dy = ys[j] - me.py;
-        const double rvx = vxs[j] - me.vx;
-        const double rvy = vys[j] - me.vy;
+        const double2 c = pos[j], cv = vel[j];
+        const double dx = c.x - me.px;
+        const double dy = c.y - me.py;
+        const double rvx = cv.x - me.vx;
+        const double rvy = cv.y - me.vy;
         const double qa = rvx * rvx + rvy * rvy;
         const double d2 = dx * dx + dy * dy;
         const double qb = 2.0 * (rvx * dx + rvy * dy);
@@ -287,7 +289,8 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 6) step_warp_kernel(StepArgs a)
         PairIn p;
         p.px = w.px[o]; p.py = w.py[o]; p.vx = w.vx[o]; p.vy = w.vy[o];
         p.pfx = w.pfx[o]; p.pfy = w.pfy[o]; p.id = w.id[o];
-        p.ox = xs[j]; p.oy = ys[j]; p.ovx = vxs[j]; p.ovy = vys[j]; p.oid = ids[j];
+        const double2 c = pos[j], cv = vel[j];
+        p.ox = c.x; p.oy = c.y; p.ovx = cv.x; p.ovy = cv.y; p.oid = ids[j];
         pair_force_literal(p, w.ti[o], a.groups[w.grp[o]], qx, qy);
       };
       // Every owner's pairs take one contiguous segment of a list, in canonical neighbour order (slice 0, 1, 2;
@@ -337,7 +340,8 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 6) step_warp_kernel(StepArgs a)
           const uint32_t o = w.lo[e];
           const uint32_t j = w.lj[e];
           double qx, qy;
-          pair_force_yield(load_pre(o), w.px[o], w.py[o], w.vx[o], w.vy[o], xs[j], ys[j], vxs[j], vys[j], w.ti[o],
+          const double2 c = pos[j], cv = vel[j];
+          pair_force_yield(load_pre(o), w.px[o], w.py[o], w.vx[o], w.vy[o], c.x, c.y, cv.x, cv.y, w.ti[o],
                            a.groups[w.grp[o]], qx, qy);
           w.sfx[e] = qx;
           w.sfy[e] = qy;
@@ -345,7 +349,8 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 6) step_warp_kernel(StepArgs a)
         for (uint32_t e = lane; e < nB; e += 32) {  // weight-0 pairs: prove the contribution is (+-0, +-0)
           const uint32_t o = w.lo[SW_CAP + e];
           const uint32_t j = w.lj[SW_CAP + e];
-          if (!pair_force_w0_is_zero(load_pre(o), xs[j], ys[j], vxs[j], vys[j], w.ti[o])) {
+          const double2 c = pos[j], cv = vel[j];
+          if (!pair_force_w0_is_zero(load_pre(o), c.x, c.y, cv.x, cv.y, w.ti[o])) {
             // contributes NaN or +-0 per component (rcs_math.cuh): NaN is order-independent
             double qx, qy;
             literal(o, j, qx, qy);
