@@ -3,7 +3,7 @@
 //   bin_count -> scan (3 small kernels, warp-shuffle scans) -> scatter_perm -> sort_cells_by_id
 //   -> gather_sorted -> step_kernel (radius query + Zanlungo + explicit Euler, fused)
 //
-// Data layout: structure-of-arrays f64 positions / velocities, u64 ids, u32 group / waypoint,
+// Data layout: structure of arrays -- double2 positions, double2 velocities, u64 ids, u32 group / waypoint --
 // physically re-sorted every step into canonical (cell index, agent id) order, so the reference's
 // scan `for x in left..=right { for y in bottom..=top }` (location_hash_2d.rs:245-246) is, for each
 // x, one contiguous slice of the sorted arrays (the cell index is x-major, :59).
