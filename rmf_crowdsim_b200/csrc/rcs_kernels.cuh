@@ -1056,11 +1056,6 @@ __global__ void route_set_target_kernel(uint32_t m, const uint64_t* __restrict__
   wp[sl] = (wp[sl] & WP_MASK) | (1u << WP_ROUTE_SHIFT);
 }
 
-__global__ void mask_u32_kernel(uint64_t n, uint32_t* p, uint32_t mask) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] &= mask;
-}
-
 __global__ void fill_u32_kernel(uint64_t n, uint32_t* p, uint32_t v) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -1132,17 +1127,6 @@ __global__ void compact_keep_kernel(uint32_t n_ub, const uint32_t* __restrict__ 
   out.grp[k] = in.grp[i];
   out.wp[k] = in.wp[i];
   if (in.pv) out.pv[k] = in.pv[i];
-}
-
-// keep flags beyond the live count must be 0 before the scan
-__global__ void clear_keep_tail_kernel(uint32_t n_ub, const uint32_t* __restrict__ n_ptr, uint32_t* keep) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_ub && i >= *n_ptr) keep[i] = 0u;
-}
-
-__global__ void set_count_kernel(uint32_t* dst, const uint32_t* src, const DevStatus* status) {
-  if (status && status->failed) return;
-  *dst = *src;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -35,7 +35,6 @@ namespace rcs {
 constexpr int SW_WARPS = 4;            // warps per block
 constexpr uint32_t SW_CAP = 128;       // stage-3 pair lists (A: evaluate, B: prove zero); >= 3 * SW_SLICE_MAX
 constexpr uint32_t SW_SLICE_MAX = 32;  // candidates per stencil column on the cooperative path (mask width)
-constexpr uint32_t SW_NONE = 0xffffu;
 
 struct WarpShared {
   double px[32], py[32], vx[32], vy[32], rr[32];                              // owners (stages 2 and 3)
