@@ -117,8 +117,9 @@ def make_scene(workload: str, variant: str, lp_none: bool = False):
         if lp_none:
             sc.lp = ("none",)
         return sc
-    if workload.startswith("side"):
-        return SC.uniform_crowd(int(workload[4:]), variant, margin=64.0, lp=lp)
+    if workload.startswith("side"):  # sideN[:cell]: N x N agents, optional hash cell size (default 2 m = eyesight)
+        side, _, cell = workload[4:].partition(":")
+        return SC.uniform_crowd(int(side), variant, margin=64.0, lp=lp, cell=float(cell) if cell else 2.0)
     raise SystemExit(f"unknown workload {workload}")
 
 
