@@ -181,13 +181,25 @@ static int upload_counts(rcs_sim* s) {
 
 // A1/A2 of SURVEY.md section 8a.  Bins the agents [first, cnt[CNT_TOT]) of `cur` into the histogram
 // (which the caller has zeroed, or which already holds the owned agents of a strip).
-static int bin_agents(rcs_sim* s, uint32_t n_ub, const uint32_t* first, uint32_t launch_n = 0) {
+static int bin_agents(rcs_sim* s, uint32_t n_ub, const uint32_t* first, uint32_t launch_n = 0, bool pack = false) {
   if (!n_ub) return RCS_OK;
   if (!launch_n) launch_n = n_ub;  // threads to launch: fewer than n_ub when only the tail behind *first is binned
+  PackArgs pk{};
+  if (pack) {  // strips, owned pass: the boundary columns go to the send buffers on the way
+    pk.enabled = 1u;
+    pk.nx = (uint32_t)s->grid.nx;
+    pk.width = s->halo_width;
+    pk.has_left = s->rank > 0;
+    pk.has_right = s->rank + 1 < s->world;
+    pk.st = s->strip;
+    pk.left = s->send_l.buf;
+    pk.right = s->send_r.buf;
+    pk.cur = s->cur;
+  }
   bin_count_kernel<<<blocks_for(launch_n, 256), 256, 0, s->stream>>>(s->grid, n_ub, first, s->cnt + CNT_TOT, s->cur.pos,
                                                                  s->cur_has_dead ? s->keep : nullptr,
                                                                  s->cellid, s->cell_count, s->cell_lo, s->cell_hi,
-                                                                 s->d_status);
+                                                                 pk, s->d_status);
   s->launches += 1;
   CU_TRY(s, cudaGetLastError());
   return RCS_OK;

@@ -5,7 +5,7 @@
 //
 //   phase A   begin_step                              reset per-step counters
 //             ss_probe + ss_spawn          [sources]  lib.rs:199-254: spawn at most one agent per source
-//             bin owned + halo pack         [strips]  boundary columns -> send buffers
+//             bin owned (+ halo pack)       [strips]  boundary columns -> send buffers, fused into the binning pass
 //   exchange  NCCL send/recv | peer copies  [strips]
 //   phase B   halo unpack + bin ghosts      [strips]  ghosts appended behind the owned agents
 //             bin -> scan -> scatter -> sort cells by id -> gather      LocationHash2D rebuild (A1, A2)
@@ -145,7 +145,8 @@ static int step_phase_a(rcs_sim* s, double dt) {
   if (rc) return rc;
   rc = upload_counts(s);
   if (rc) return rc;
-  begin_step_kernel<<<1, 1, 0, s->stream>>>(s->d_status, s->cnt);
+  begin_step_kernel<<<1, 1, 0, s->stream>>>(s->d_status, s->cnt, s->strip.enabled ? s->send_l.buf.count : nullptr,
+                                            s->strip.enabled ? s->send_r.buf.count : nullptr);
   s->launches += 1;
   if (s->n_sources_alive) {
     const uint32_t n_before = s->n_ub;
@@ -169,14 +170,8 @@ static int step_phase_a(rcs_sim* s, double dt) {
         CU_TRY(s, cudaStreamWaitEvent(s->stream, nb->ev_copied, 0));
     rc = clear_histogram(s);
     if (rc) return rc;
-    rc = bin_agents(s, s->n_ub, nullptr);
+    rc = bin_agents(s, s->n_ub, nullptr, 0, true);  // owned agents: histogram + halo pack in one pass
     if (rc) return rc;
-    const int has_l = s->rank > 0, has_r = s->rank + 1 < s->world;
-    halo_header_kernel<<<1, 1, 0, s->stream>>>(s->send_l.buf, s->send_r.buf, s->d_status);
-    halo_pack_kernel<<<blocks_for(s->n_ub, 256), 256, 0, s->stream>>>(
-        s->n_ub, s->cnt + CNT_CUR, s->cur, s->cellid, (uint32_t)s->grid.nx, s->strip, s->halo_width, s->send_l.buf,
-        s->send_r.buf, has_l, has_r, s->d_status);
-    s->launches += 2;
     if (s->ev_packed) CU_TRY(s, cudaEventRecord(s->ev_packed, s->stream));
   }
   CU_TRY(s, cudaGetLastError());

@@ -58,11 +58,33 @@ struct StripDev {
 
 // Structure of arrays with the two f64 components of a vector interleaved, so that every position / velocity
 // moves with one 16-byte access.
+// Strips: a halo buffer is [count u32, failed u32, pad to 64 B][pos][vel][id][meta][pv], each `cap` entries.
+// Packed order is arbitrary (atomic append); the receiver re-sorts.
+struct HaloBuf {
+  uint32_t* count;
+  double2 *pos, *vel;
+  unsigned long long* id;
+  unsigned long long* meta;  // grp | wp << 32
+  double2* pv;
+  uint32_t cap;
+};
+
 struct AgentArrays {
   double2 *pos, *vel;
   uint64_t* id;
   uint32_t *grp, *wp;
   double2* pv;  // host-planner preferred velocities; NaN in .x = None.  nullptr if no host planner exists
+};
+
+// Halo packing fused into the binning pass over the owned agents of a strip: an agent whose insert cell lies in
+// the outermost `width` columns is appended to the send buffer of that side (both, on a very narrow strip).
+struct PackArgs {
+  uint32_t enabled;
+  uint32_t nx, width;
+  int has_left, has_right;
+  StripDev st;
+  HaloBuf left, right;
+  AgentArrays cur;
 };
 
 constexpr int SCAN_THREADS = 256;
@@ -81,7 +103,7 @@ __global__ void bin_count_kernel(GridDev g, uint32_t n_ub, const uint32_t* __res
                                  const uint32_t* __restrict__ last, const double2* __restrict__ pos,
                                  const uint32_t* __restrict__ keep,
                                  uint32_t* __restrict__ cellid, uint32_t* __restrict__ cell_count, uint64_t cell_lo,
-                                 uint64_t cell_hi, DevStatus* status) {
+                                 uint64_t cell_hi, PackArgs pk, DevStatus* status) {
   if (status->failed) return;
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x + (first ? *first : 0u);
   if (i >= n_ub || i >= *last) return;
@@ -101,6 +123,26 @@ __global__ void bin_count_kernel(GridDev g, uint32_t n_ub, const uint32_t* __res
     }
     cellid[i] = (uint32_t)idx;
     atomicAdd(&cell_count[idx], 1u);
+    if (pk.enabled) {
+      const uint32_t cx = (uint32_t)idx / pk.nx;
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        const bool send = side == 0 ? (pk.has_left && cx < pk.st.c0 + pk.width)
+                                    : (pk.has_right && cx + pk.width >= pk.st.c1);
+        if (!send) continue;
+        const HaloBuf& b = side == 0 ? pk.left : pk.right;
+        const uint32_t k = atomicAdd(b.count, 1u);
+        if (k >= b.cap) {
+          atomicAdd(&status->capacity_err, 1u);
+          continue;
+        }
+        b.pos[k] = p;
+        b.vel[k] = pk.cur.vel[i];
+        b.id[k] = pk.cur.id[i];
+        b.meta[k] = (unsigned long long)pk.cur.grp[i] | ((unsigned long long)pk.cur.wp[i] << 32);
+        if (pk.cur.pv) b.pv[k] = pk.cur.pv[i];
+      }
+    }
   } else {
     // only reachable through snapshot injection; steps never commit an out-of-bounds position
     cellid[i] = CELL_DEAD;
@@ -1069,7 +1111,15 @@ __global__ void fill_f64_kernel(uint64_t n, double* p, double v) {
 // Step bookkeeping on the device.  Steps are enqueued asynchronously; a step that fails makes every
 // later kernel of the handle a no-op (status->failed is sticky until rcs_sync reports it).
 // ---------------------------------------------------------------------------------------------
-__global__ void begin_step_kernel(DevStatus* st, uint32_t* cnt) {
+// strips: also resets the headers of the two send buffers: [0] = number of packed agents, [1] = "this rank has
+// failed" (so that a failure reaches the neighbours with the next exchange and the whole job stops within `world` steps)
+__global__ void begin_step_kernel(DevStatus* st, uint32_t* cnt, uint32_t* send_l_hdr, uint32_t* send_r_hdr) {
+  if (send_l_hdr) {
+    send_l_hdr[0] = 0u;
+    send_r_hdr[0] = 0u;
+    send_l_hdr[1] = st->failed;
+    send_r_hdr[1] = st->failed;
+  }
   if (st->failed) return;
   st->oob_count = 0;
   st->nonfinite_count = 0;
@@ -1253,50 +1303,6 @@ __global__ void ss_spawn_kernel(GridDev g, const SourceSinkDev* __restrict__ ss,
 // Strips: halo pack / unpack.  A halo buffer is [count u32, pad][pos][vel][id][meta][pv],
 // each array `cap` entries.  Packed order is arbitrary (atomic append); the receiver re-sorts.
 // ---------------------------------------------------------------------------------------------
-struct HaloBuf {
-  uint32_t* count;
-  double2 *pos, *vel;
-  unsigned long long* id;
-  unsigned long long* meta;  // grp | wp << 32
-  double2* pv;
-  uint32_t cap;
-};
-
-__global__ void halo_pack_kernel(uint32_t n_ub, const uint32_t* __restrict__ n_ptr, AgentArrays cur,
-                                 const uint32_t* __restrict__ cellid, uint32_t nx, StripDev st, uint32_t width,
-                                 HaloBuf left, HaloBuf right, int has_left, int has_right, DevStatus* status) {
-  if (status->failed) return;
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_ub || i >= *n_ptr) return;
-  const uint32_t c = cellid[i];
-  if (c == CELL_DEAD) return;
-  const uint32_t cx = c / nx;
-  for (int side = 0; side < 2; ++side) {
-    const bool send = side == 0 ? (has_left && cx < st.c0 + width) : (has_right && cx + width >= st.c1);
-    if (!send) continue;
-    HaloBuf& b = side == 0 ? left : right;
-    const uint32_t k = atomicAdd(b.count, 1u);
-    if (k >= b.cap) {
-      atomicAdd(&status->capacity_err, 1u);
-      continue;
-    }
-    b.pos[k] = cur.pos[i];
-    b.vel[k] = cur.vel[i];
-    b.id[k] = cur.id[i];
-    b.meta[k] = (unsigned long long)cur.grp[i] | ((unsigned long long)cur.wp[i] << 32);
-    if (cur.pv) b.pv[k] = cur.pv[i];
-  }
-}
-
-// header of a send buffer: [0] = number of packed agents, [1] = "this rank has failed" (so that a failure
-// reaches the neighbours with the next exchange and the whole job stops within `world` steps)
-__global__ void halo_header_kernel(HaloBuf left, HaloBuf right, const DevStatus* status) {
-  left.count[0] = 0u;
-  right.count[0] = 0u;
-  left.count[1] = status->failed;
-  right.count[1] = status->failed;
-}
-
 // appends the ghosts of both received buffers after the owned agents; cnt[CNT_TOT] = owned + ghosts
 __global__ void halo_unpack_kernel(AgentArrays cur, uint32_t* __restrict__ keep, uint32_t cap, HaloBuf left,
                                    HaloBuf right, int has_left, int has_right, uint32_t* cnt, DevStatus* status) {

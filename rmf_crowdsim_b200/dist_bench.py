@@ -66,7 +66,7 @@ def run(args) -> None:
     n_own = int(m.sum())
     # room for the owned agents, three ghost columns per side and the churn of a long committed run
     per_col = int(round(n_total ** 0.5)) * scene.cell  # agents per cell column at spacing 1 m
-    halo_cap = int(4 * per_col * 1.5) + 4096
+    halo_cap = int(3.3 * per_col) + 2048  # three columns per side (W = ring + reach) and 10 % slack
     cap = int(n_own * 1.05) + 2 * halo_cap + 4096
     idx = S.LocationHash2D(scene.width, scene.height, scene.cell, scene.offset, capacity=cap, device=local)
     sim = StripSimulation(idx, rank, world, nccl_id, halo_capacity=halo_cap)
