@@ -125,10 +125,8 @@ static int strip_setup(rcs_sim* s, int rank, int world, uint64_t halo_capacity) 
     if (rc) return rc;
   }
   CU_TRY(s, dalloc(&s->srt_cell, s->cap + 16));
-  if (!s->cur.pv) {
-    // ghosts carry the host-planner preferred velocity only when such a planner exists; the halo buffers
-    // always have room for it
-  }
+  // (ghosts carry the host-planner preferred velocity only when such a planner exists; the halo buffers always
+  // have room for it)
   s->strip = st;
   s->rank = rank;
   s->world = world;

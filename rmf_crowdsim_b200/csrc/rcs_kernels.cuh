@@ -853,7 +853,8 @@ __global__ void __launch_bounds__(256) step_stream_kernel(StepArgs a) {
 }
 
 // Finishes the agents the warp-cooperative kernel put on the slow list (stencil wider than three
-// columns or more than SW_MAXC candidates).  Grid-stride over the device-side count.
+// columns, more than 32 candidates in a column, ids >= 2^53, planners without the weight-0 proof).  Grid-stride over
+// the device-side count.
 __global__ void __launch_bounds__(128) step_slow_kernel(StepArgs a) {
   if (a.status->failed) return;
   const uint32_t n_slow = a.status->slow_count;
