@@ -145,6 +145,11 @@ static int step_phase_a(rcs_sim* s, double dt) {
   if (rc) return rc;
   rc = upload_counts(s);
   if (rc) return rc;
+  // single-process transport: the neighbours must have fetched the previous step's send buffers before their
+  // headers are reset (with NCCL the sends are ordered on this very stream)
+  for (rcs_sim* nb : s->local_group)
+    if (nb && nb != s && std::abs(nb->rank - s->rank) == 1 && nb->ev_copied)
+      CU_TRY(s, cudaStreamWaitEvent(s->stream, nb->ev_copied, 0));
   begin_step_kernel<<<1, 1, 0, s->stream>>>(s->d_status, s->cnt, s->strip.enabled ? s->send_l.buf.count : nullptr,
                                             s->strip.enabled ? s->send_r.buf.count : nullptr);
   s->launches += 1;
@@ -164,10 +169,6 @@ static int step_phase_a(rcs_sim* s, double dt) {
     s->n_ub = (uint32_t)s->cap;
     rc = strip_halo_width(s);  // also narrows [cell_lo, cell_hi) to the strip and its halo
     if (rc) return rc;
-    // the neighbours must have fetched the previous step's send buffers (single-process transport)
-    for (rcs_sim* nb : s->local_group)
-      if (nb && nb != s && std::abs(nb->rank - s->rank) == 1 && nb->ev_copied)
-        CU_TRY(s, cudaStreamWaitEvent(s->stream, nb->ev_copied, 0));
     rc = clear_histogram(s);
     if (rc) return rc;
     rc = bin_agents(s, s->n_ub, nullptr, 0, true);  // owned agents: histogram + halo pack in one pass
