@@ -279,7 +279,7 @@ def run_gpu_single(args):
         except Exception:
             traffic = None
     roofline = {
-        "bound": "hbm", "kernel": "step_warp_kernel + step_slow_kernel (radius query + Zanlungo + Euler, fused)",
+        "bound": "hbm", "kernel": "step_warp_kernel + step_aside_kernel (radius query + Zanlungo + Euler, fused)",
         "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
         "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "peak_source": how, "traffic": traffic,
         "algorithmic_bytes_per_agent_step": algo, "kernel_ms": k_ms, "kernel_share_of_step": k_ms * K / total_ms,

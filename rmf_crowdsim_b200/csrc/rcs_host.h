@@ -80,7 +80,7 @@ struct rcs_sim {
   uint32_t n_ub = 0;  // upper bound used to size launches while steps with churn are in flight
   rcs::AgentArrays cur{}, srt{};
   uint32_t *cellid = nullptr, *perm = nullptr, *cell_count = nullptr, *cell_start = nullptr, *cursor = nullptr;
-  uint32_t *tile_sums = nullptr, *scan_total = nullptr, *big_list = nullptr, *slow_list = nullptr;
+  uint32_t *tile_sums = nullptr, *scan_total = nullptr, *big_list = nullptr, *slow_list = nullptr, *wide_list = nullptr;
   uint32_t* srt_cell = nullptr;  // strips: insert cell of every sorted agent
   uint4* slices = nullptr;       // per sorted agent: candidate slices of its radius query (gather_sorted_kernel)
   uint32_t* keep = nullptr;      // churn: 0 = the entry leaves (sink reached, migrated, ghost); dropped by the next sort

@@ -79,6 +79,7 @@ int rcs_sim_create(const rcs_sim_desc* desc, rcs_sim** out) {
   CR_TRY(dalloc(&s->scan_total, 4));
   CR_TRY(dalloc(&s->big_list, 4096));
   CR_TRY(dalloc(&s->slow_list, s->cap + 16));
+  CR_TRY(dalloc(&s->wide_list, s->cap + 16));
   CR_TRY(dalloc(&s->keep, s->cap + 16));
   CR_TRY(dalloc(&s->slices, s->cap + 16));
   CR_TRY(dalloc(&s->cnt, CNT_N));
@@ -115,7 +116,7 @@ void rcs_sim_destroy(rcs_sim* s) {
   cudaFree(s->d_bad); cudaFree(s->d_bad2); cudaFree(s->slot_of_id); cudaFree(s->id_rank); cudaFree(s->presence);
   cudaFree(s->tr_ti); cudaFree(s->tr_fx); cudaFree(s->tr_fy); cudaFree(s->tr_nbc); cudaFree(s->tr_nbo);
   cudaFree(s->tr_nbids); cudaFree(s->tr_id); cudaFree(s->tr_own); cudaFree(s->stage); cudaFree(s->flush_buf);
-  cudaFree(s->slow_list); cudaFree(s->keep); cudaFree(s->slices); cudaFree(s->cnt); cudaFree(s->d_next_id); cudaFree(s->srt_cell);
+  cudaFree(s->slow_list); cudaFree(s->wide_list); cudaFree(s->keep); cudaFree(s->slices); cudaFree(s->cnt); cudaFree(s->d_next_id); cudaFree(s->srt_cell);
   cudaFree(s->d_sources); cudaFree(s->d_ss_wp); cudaFree(s->d_blocked); cudaFree(s->d_sg_start);
   cudaFree(s->d_sg_items); cudaFree(s->ev_spawn_id); cudaFree(s->ev_destroyed); cudaFree(s->ev_spawn_xy);
   dist_teardown(s);

@@ -269,8 +269,9 @@ static void launch_step_kernel(rcs_sim* s, const StepArgs& a, uint32_t n_ub, boo
   }
   if (sorted_input && s->opt_step_kernel != 1) {
     step_warp_kernel<<<blocks_for(n_ub, 32 * SW_WARPS), 32 * SW_WARPS, 0, s->stream>>>(a);
-    // agents with a stencil wider than three columns or very crowded cells (device-side list)
-    step_slow_kernel<<<148 * 2, 128, 0, s->stream>>>(a);
+    // the agents it left aside (device-side lists): stencils wider than three columns or crowded columns go to
+    // the chunked cooperative kernel, ids >= 2^53 and planners without the weight-0 proof to the sequential one
+    step_aside_kernel<<<148 * 4, 32 * SW_WARPS, 0, s->stream>>>(a);
     s->launches += 2;
   } else if (!sorted_input && s->opt_step_kernel != 1) {
     step_stream_kernel<<<blocks_for((n_ub + 1) / 2, 256), 256, 0, s->stream>>>(a);  // NoLocalPlan only, no churn

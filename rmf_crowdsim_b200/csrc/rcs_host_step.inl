@@ -103,6 +103,7 @@ static StepArgs make_step_args(rcs_sim* s, const AgentArrays& in, const AgentArr
   }
   a.cnt = s->cnt;
   a.slow_list = s->slow_list;
+  a.wide_list = s->wide_list;
   a.slices = full_out ? s->slices : nullptr;
   a.routes = s->d_routes;
   a.route_thr2 = radius_threshold(1e-1);

@@ -24,6 +24,7 @@ struct DevStatus {
   unsigned int spawned;         // agents spawned by source sinks in this step
   unsigned int destroyed;       // agents removed at sinks in this step
   unsigned int slow_count;      // agents handed to the sequential kernel by the warp-cooperative kernel
+  unsigned int wide_count;      // agents handed to step_aside_kernel's cooperative part (wide or crowded stencils)
   unsigned long long first_oob_id;
   unsigned long long finite_tti;
   unsigned long long neighbour_total;
@@ -468,6 +469,7 @@ struct StepArgs {
   unsigned long long* ev_destroyed;  // (id, step) pairs of agents removed at sinks
   uint32_t ev_cap;
   uint32_t* slow_list;             // warp kernel: agents left to the sequential kernel
+  uint32_t* wide_list;             // warp kernel: agents left to the chunked cooperative routine
   const uint4* slices;             // candidate slices prepared by gather_sorted_kernel (sorted path only)
   const double* routes;            // HL_ROUTE polylines, interleaved x,y
   double route_thr2;               // smallest double T with sqrt(T) >= 1e-1 (rmf/mod.rs:202)
@@ -852,18 +854,6 @@ __global__ void __launch_bounds__(256) step_stream_kernel(StepArgs a) {
   }
 }
 
-// Finishes the agents the warp-cooperative kernel put on the slow list (stencil wider than three
-// columns, more than 32 candidates in a column, ids >= 2^53, planners without the weight-0 proof).  Grid-stride over
-// the device-side count.
-__global__ void __launch_bounds__(128) step_slow_kernel(StepArgs a) {
-  if (a.status->failed) return;
-  const uint32_t n_slow = a.status->slow_count;
-  uint32_t cand = 0, nbc = 0, finite = 0;
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_slow; k += gridDim.x * blockDim.x)
-    step_one_agent(a, a.slow_list[k], cand, nbc, finite);
-  warp_stats(a, cand, nbc, finite);
-}
-
 // Trace: neighbour ids in list order (lib.rs:281-286) as CSR, offsets from an exclusive scan of nb_count.
 __global__ void trace_neighbours_kernel(StepArgs a, const uint32_t* __restrict__ nb_offsets,
                                         uint64_t* __restrict__ nb_ids) {
@@ -1131,6 +1121,7 @@ __global__ void begin_step_kernel(DevStatus* st, uint32_t* cnt, uint32_t* send_l
   st->spawned = 0;
   st->destroyed = 0;
   st->slow_count = 0;
+  st->wide_count = 0;
   st->first_oob_id = ~0ull;
   st->finite_tti = 0;
   st->neighbour_total = 0;

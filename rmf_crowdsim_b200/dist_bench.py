@@ -158,7 +158,7 @@ def run(args) -> None:
             },
             "e2e": e2e, "gpu_launches": int(agg[6].item()),
             "roofline": {
-                "bound": "hbm", "kernel": "step_warp_kernel (+ step_slow_kernel) per rank, slowest rank",
+                "bound": "hbm", "kernel": "step_warp_kernel (+ step_aside_kernel) per rank, slowest rank",
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "peak_source": how, "traffic": None,
                 "algorithmic_bytes_per_agent_step": algo, "kernel_ms": k_ms,

@@ -139,7 +139,7 @@ def run(args) -> None:
             "nonfinite": int(st.nonfinite_count), "oob": int(st.oob_count),
         },
         "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "step_warp_kernel + step_slow_kernel", "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": "step_warp_kernel + step_aside_kernel", "achieved": achieved,
                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (achieved / peaks["hbm_gbs"]) if achieved else None,
                      "peak_source": how, "traffic": None, "algorithmic_bytes_per_agent_step": algo, "kernel_ms": k_ms,
                      "kernel_share_of_step": k_ms * K / total_ms},

@@ -283,6 +283,48 @@ def test_warp_cooperative_kernel_is_bit_identical_to_thread_per_agent(variant):
     assert sims[0].stats().candidate_total == sims[1].stats().candidate_total
 
 
+@pytest.mark.parametrize("cell,eyesight,s", [
+    (1.0, 2.0, 1.0),    # 5 stencil columns: two rounds of chunks
+    (0.5, 2.2, 1.0),    # 9-10 columns, mostly empty cells
+    (4.0, 2.0, 0.5),    # 64 agents per cell: up to 4 chunks per column, 3 columns
+    (8.0, 3.0, 1.0),    # coarse cells, 64-128 candidates per column
+    (3.0, 2.0, 1.0),    # mixed: some agents fit the three-slice path, some do not
+])
+def test_wide_and_crowded_stencils_are_bit_identical_to_thread_per_agent(cell, eyesight, s):
+    """step_aside_kernel (chunked stencil columns, two passes) against the sequential routine of step_kernel: same
+    neighbour lists, t_i, forces, state, statistics -- every bit."""
+    from rmf_crowdsim_b200 import _native as N
+
+    rng = np.random.default_rng(17)
+    scene = SC.uniform_crowd(72, "shuffled", s=s, cell=cell, eyesight=eyesight, margin=16.0, seed=9,
+                             lp=("zanlungo", 0.05, 1.0, 0.0, 0.5, 1.0, 0.1))
+    scene.vxy = scene.vxy + rng.uniform(-0.3, 0.3, size=scene.vxy.shape)
+    scene.dt = (0, 10_000_000)  # nobody gets inside another agent's radius within the two steps
+    sims = []
+    for kern in (1, 0):
+        g = SC.build_simulation(scene)
+        g.set_option(N.RCS_OPT_STEP_KERNEL, kern)
+        g.set_trace(True)
+        sims.append(g)
+    finite = 0
+    for _ in range(2):
+        for g in sims:
+            g.step(R.Duration(*scene.dt))
+        ta, tb = sims[0].read_trace(), sims[1].read_trace()
+        for k in ("id", "nb_offsets", "nb_ids"):
+            assert np.array_equal(ta[k], tb[k]), k
+        for k in ("t_i", "fx", "fy"):
+            assert np.array_equal(ta[k].view(np.uint64), tb[k].view(np.uint64)), k
+        finite += int(np.isfinite(ta["t_i"]).sum())
+        sa, sb = sims[0].read_state(), sims[1].read_state()
+        for k in ("x", "y", "vx", "vy"):
+            assert np.array_equal(sa[k].view(np.uint64), sb[k].view(np.uint64)), k
+    assert finite > 100
+    sta, stb = sims[0].stats(), sims[1].stats()
+    assert sta.neighbour_total == stb.neighbour_total and sta.candidate_total == stb.candidate_total
+    assert sta.finite_tti_count == stb.finite_tti_count
+
+
 def test_more_oversized_cells_than_the_big_cell_list_holds():
     """4900 cells with 40 agents each (> 32 per cell, > 4096 such cells): the block sorter sweeps all cells and
     storage order is still canonical (cell, then ascending id)."""
