@@ -225,6 +225,7 @@ static int sort_into_srt(rcs_sim* s, uint32_t n_ub) {
       sort_cells_by_id_kernel<<<blocks_for(len, 128), 128, 0, s->stream>>>(lo, hi, s->cell_start, s->cur.id, s->perm,
                                                                            s->big_list, 4096, s->d_status);
     sort_big_cells_kernel<<<148, 1024, 0, s->stream>>>(lo, hi, s->cell_start, s->cur.id, s->perm, s->slow_list,
+                                                       s->wide_list,
                                                        s->big_list, 4096, s->d_status);
     gather_sorted_kernel<<<blocks_for(n_ub, 256), 256, 0, s->stream>>>(
         n_ub, s->perm, s->cur, s->srt, s->cellid, s->strip.enabled ? s->srt_cell : nullptr, n_sorted_ptr(s),

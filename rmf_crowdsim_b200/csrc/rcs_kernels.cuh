@@ -25,6 +25,7 @@ struct DevStatus {
   unsigned int destroyed;       // agents removed at sinks in this step
   unsigned int slow_count;      // agents handed to the sequential kernel by the warp-cooperative kernel
   unsigned int wide_count;      // agents handed to step_aside_kernel's cooperative part (wide or crowded stencils)
+  unsigned int sort_ticket;     // sort_big_cells_kernel: blocks done with a grid-ranked cell (returns to 0)
   unsigned long long first_oob_id;
   unsigned long long finite_tti;
   unsigned long long neighbour_total;
@@ -330,32 +331,70 @@ __global__ void sort_cells_by_id_kernel(uint64_t cell_lo, uint64_t cell_hi, cons
   for (uint32_t k = 0; k < m; ++k) perm[s + k] = p[k];
 }
 
-// One block per oversized cell: rank = number of smaller ids (ids are unique), O(m^2 / threads), keys staged in
-// shared memory when the cell holds at most BIG_SMEM_KEYS agents.  The cells come from big_list; if more cells
-// were oversized than the list holds (big_cells > big_cap) every block sweeps a share of ALL cells instead.
+// One block per oversized cell: rank = number of smaller ids (ids are unique), O(m^2 / threads) compares against
+// keys staged in shared memory, BIG_SMEM_KEYS at a time.  Cells beyond that size -- in practice cell 0, where the
+// reference files every agent whose position went non-finite -- are ranked by the whole grid (rank_huge_cell).
+// The cells come from big_list; if more cells were oversized than the list holds (big_cells > big_cap) every
+// block sweeps a share of ALL cells instead, whatever their size (ranks accumulate tile by tile in `ranks`).
 constexpr uint32_t BIG_SMEM_KEYS = 4096;
 
 __device__ __forceinline__ void sort_one_big_cell(uint32_t s, uint32_t e, const uint64_t* __restrict__ id,
                                                   uint32_t* __restrict__ perm, uint32_t* __restrict__ scratch,
-                                                  unsigned long long* skeys) {
+                                                  uint32_t* __restrict__ ranks, unsigned long long* skeys) {
   const uint32_t m = e - s;
-  const bool in_smem = m <= BIG_SMEM_KEYS;
-  if (in_smem)
-    for (uint32_t k = threadIdx.x; k < m; k += blockDim.x) skeys[k] = id[perm[s + k]];
-  __syncthreads();
-  for (uint32_t k = threadIdx.x; k < m; k += blockDim.x) {
-    const uint64_t kk = in_smem ? skeys[k] : id[perm[s + k]];
-    uint32_t rank = 0;
-    if (in_smem) {
-      for (uint32_t j = 0; j < m; ++j) rank += (skeys[j] < kk) ? 1u : 0u;
-    } else {
-      for (uint32_t j = s; j < e; ++j) rank += (id[perm[j]] < kk) ? 1u : 0u;
+  for (uint32_t t0 = 0; t0 < m; t0 += BIG_SMEM_KEYS) {
+    const uint32_t tl = min(BIG_SMEM_KEYS, m - t0);
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < tl; j += blockDim.x) skeys[j] = id[perm[s + t0 + j]];
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < m; k += blockDim.x) {  // a thread only ever touches its own entries of ranks
+      const uint64_t kk = id[perm[s + k]];
+      uint32_t rank = t0 ? ranks[s + k] : 0u;
+      for (uint32_t j = 0; j < tl; ++j) rank += (skeys[j] < kk) ? 1u : 0u;
+      ranks[s + k] = rank;
     }
-    scratch[s + rank] = perm[s + k];
   }
+  for (uint32_t k = threadIdx.x; k < m; k += blockDim.x) scratch[s + ranks[s + k]] = perm[s + k];
   __syncthreads();
   for (uint32_t k = s + threadIdx.x; k < e; k += blockDim.x) perm[k] = scratch[k];
   __syncthreads();
+}
+
+// A cell beyond the shared-memory tile, ranked by the whole grid: a block takes HUGE_ELEMS elements at a time, its
+// 32 warps split the keys of every tile between them (all lanes of a warp read the same key: a broadcast), partial
+// ranks are added up in shared memory.  Results go to scratch; the block that finishes last copies them back.
+constexpr uint32_t HUGE_ELEMS = 64;
+
+__device__ __forceinline__ void rank_huge_cell(uint32_t s, uint32_t e, const uint64_t* __restrict__ id,
+                                               const uint32_t* __restrict__ perm, uint32_t* __restrict__ scratch,
+                                               unsigned long long* skeys, uint32_t (*partial)[HUGE_ELEMS]) {
+  const uint32_t m = e - s;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, nwarps = blockDim.x >> 5;
+  for (uint32_t k0 = blockIdx.x * HUGE_ELEMS; k0 < m; k0 += gridDim.x * HUGE_ELEMS) {  // block-uniform
+    const uint32_t kA = k0 + lane, kB = k0 + lane + 32u;
+    const uint64_t keyA = kA < m ? id[perm[s + kA]] : 0ull, keyB = kB < m ? id[perm[s + kB]] : 0ull;
+    uint32_t rA = 0, rB = 0;
+    for (uint32_t t0 = 0; t0 < m; t0 += BIG_SMEM_KEYS) {
+      const uint32_t tl = min(BIG_SMEM_KEYS, m - t0);
+      __syncthreads();
+      for (uint32_t j = threadIdx.x; j < tl; j += blockDim.x) skeys[j] = id[perm[s + t0 + j]];
+      __syncthreads();
+      for (uint32_t j = warp; j < tl; j += nwarps) {
+        const uint64_t key = skeys[j];
+        rA += (key < keyA) ? 1u : 0u;
+        rB += (key < keyB) ? 1u : 0u;
+      }
+    }
+    partial[warp][lane] = rA;
+    partial[warp][lane + 32u] = rB;
+    __syncthreads();
+    if (threadIdx.x < HUGE_ELEMS && k0 + threadIdx.x < m) {
+      uint32_t rank = 0;
+      for (uint32_t w = 0; w < nwarps; ++w) rank += partial[w][threadIdx.x];
+      scratch[s + rank] = perm[s + k0 + threadIdx.x];
+    }
+    __syncthreads();
+  }
 }
 
 __global__ void __launch_bounds__(1024) sort_big_cells_kernel(uint64_t cell_lo, uint64_t cell_hi,
@@ -363,20 +402,49 @@ __global__ void __launch_bounds__(1024) sort_big_cells_kernel(uint64_t cell_lo, 
                                                               const uint64_t* __restrict__ id,
                                                               uint32_t* __restrict__ perm,
                                                               uint32_t* __restrict__ scratch,
+                                                              uint32_t* __restrict__ ranks,
                                                               const uint32_t* __restrict__ big_list, uint32_t big_cap,
-                                                              const DevStatus* status) {
+                                                              DevStatus* status) {
   __shared__ unsigned long long skeys[BIG_SMEM_KEYS];
+  __shared__ uint32_t partial[32][HUGE_ELEMS];
+  __shared__ bool last_block;
   if (status->failed) return;
   const uint32_t nbig = status->big_cells;
   if (nbig <= big_cap) {
-    for (uint32_t b = blockIdx.x; b < nbig; b += gridDim.x) {
+    for (uint32_t b = blockIdx.x; b < nbig; b += gridDim.x) {  // one block per cell that fits a tile
       const uint32_t c = big_list[b];
-      sort_one_big_cell(cell_start[c], cell_start[c + 1], id, perm, scratch, skeys);
+      const uint32_t cs = cell_start[c], ce = cell_start[c + 1];
+      if (ce - cs <= BIG_SMEM_KEYS) sort_one_big_cell(cs, ce, id, perm, scratch, ranks, skeys);
+    }
+    uint32_t n_huge = 0;
+    for (uint32_t b = 0; b < nbig; ++b) {  // every block: the same cells in the same order
+      const uint32_t c = big_list[b];
+      const uint32_t cs = cell_start[c], ce = cell_start[c + 1];
+      if (ce - cs > BIG_SMEM_KEYS) {
+        rank_huge_cell(cs, ce, id, perm, scratch, skeys, partial);
+        n_huge += 1;
+      }
+    }
+    if (n_huge) {
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) last_block = atomicAdd(&status->sort_ticket, 1u) == gridDim.x - 1;
+      __syncthreads();
+      if (last_block) {  // every block's ranks are in scratch
+        __threadfence();
+        for (uint32_t b = 0; b < nbig; ++b) {
+          const uint32_t c = big_list[b];
+          const uint32_t cs = cell_start[c], ce = cell_start[c + 1];
+          if (ce - cs > BIG_SMEM_KEYS)
+            for (uint32_t k = cs + threadIdx.x; k < ce; k += blockDim.x) perm[k] = __ldcg(scratch + k);
+        }
+        if (threadIdx.x == 0) status->sort_ticket = 0u;
+      }
     }
   } else {
     for (uint64_t c = cell_lo + blockIdx.x; c < cell_hi; c += gridDim.x) {  // block-uniform bounds
       const uint32_t cs = cell_start[c], ce = cell_start[c + 1];
-      if (ce - cs > SORT_LOCAL_MAX) sort_one_big_cell(cs, ce, id, perm, scratch, skeys);
+      if (ce - cs > SORT_LOCAL_MAX) sort_one_big_cell(cs, ce, id, perm, scratch, ranks, skeys);
     }
   }
 }

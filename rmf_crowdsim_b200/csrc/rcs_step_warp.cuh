@@ -487,6 +487,18 @@ __device__ __forceinline__ void cw_next(ColumnWalk& c, const GridDev& g, const u
   c.rem -= l;
 }
 
+// Consumes what is left of the walk without looking at the candidates; returns how many there were.
+__device__ __forceinline__ uint32_t cw_skip_all(ColumnWalk& c, const GridDev& g,
+                                                const uint32_t* __restrict__ cell_start) {
+  uint32_t total = c.rem;
+  c.rem = 0u;
+  for (; c.col <= c.right; ++c.col) {
+    uint64_t c_lo, c_hi;
+    if (column_cell_range(g, c.col, c.bottom, c.top, c_lo, c_hi)) total += cell_start[c_hi + 1] - cell_start[c_lo];
+  }
+  return total;
+}
+
 // The first rounds' masks of the first pass are kept for the second one (one column of words per lane).
 constexpr uint32_t SW_WIDE_ROUNDS = 4;
 struct WideMasks {
@@ -553,6 +565,11 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 4) step_aside_kernel(StepArgs a
     ColumnWalk cw;
     if (have) cw_begin(cw, a.grid, eyesight, me.px, me.py);
     else cw_none(cw);
+    // An agent whose own position is not finite has no neighbours: every d2 is inf or NaN and fails the strict
+    // `<` of location_hash_2d.rs:251.  The reference files such agents in cell 0 (NaN as usize = 0) and their
+    // query is the whole of cell 0, so a crowd that has gone non-finite would otherwise cost the square of their
+    // number.  Only the candidate statistic still needs the slice lengths.
+    if (have && !(isfinite(me.px) && isfinite(me.py))) cand += cw_skip_all(cw, a.grid, a.cell_start);
     for (uint32_t r = 0; __any_sync(FULL, cw_more(cw)); ++r) {
       uint32_t s0, s1, s2, l0, l1, l2;
       cw_next(cw, a.grid, a.cell_start, s0, l0);

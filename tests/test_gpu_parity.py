@@ -346,6 +346,66 @@ def test_more_oversized_cells_than_the_big_cell_list_holds():
     assert len(st["id"]) == len(xy) and sim.stats().oob_count == 0
 
 
+def test_one_cell_larger_than_the_sorters_shared_memory_tile():
+    """9500 agents in one cell (> BIG_SMEM_KEYS = 4096: ranks accumulate over three key tiles) next to ordinary
+    cells -- the shape of cell 0 once a crowd has gone non-finite.  Storage order is still (cell, ascending id)."""
+    rng = np.random.default_rng(4)
+    cell = 50.0
+    big = rng.uniform(0.5, cell - 0.5, size=(9500, 2))
+    rest = rng.uniform(cell + 1.0, 4 * cell - 1.0, size=(3000, 2))
+    xy = np.concatenate([big, rest])
+    xy = xy[rng.permutation(len(xy))]
+    idx = R.LocationHash2D(4 * cell, 4 * cell, cell, (0.0, 0.0), capacity=len(xy))
+    sim = R.Simulation(idx)
+    sim.add_agents(xy, R.ConstantVelocityPlan((0.0, 0.0)), R.Zanlungo(0.05, 1.0, 0.0, 0.5, 1.0, 0.01), 0.05)
+    for _ in range(2):
+        sim.step(R.Duration(0, 1_000_000))
+    st = sim.read_state(order=R._native.RCS_ORDER_STORAGE)
+    cells = idx.cell_of(np.stack([st["x"], st["y"]], axis=1))
+    key = cells.astype(np.uint64) * np.uint64(1 << 32) + st["id"]
+    assert np.all(key[1:] > key[:-1])
+    assert np.array_equal(np.sort(st["id"]), np.arange(len(xy), dtype=np.uint64))
+
+
+def test_agents_with_non_finite_positions_pile_up_in_cell_0_and_see_nobody():
+    """NaN / inf positions are filed in cell 0 by the reference (`NaN as usize` = 0) and can have no neighbour (no d2
+    passes the strict `<`); the cooperative kernels skip their query.  Same state, neighbour lists and statistics
+    as the thread-per-agent kernel, and the finite part of the crowd is unaffected."""
+    from rmf_crowdsim_b200 import _native as N
+
+    scene = SC.uniform_crowd(64, "shuffled", margin=16.0, seed=12)
+    rng = np.random.default_rng(8)
+    bad = rng.choice(scene.n, size=400, replace=False).astype(np.uint64)
+    sims = []
+    for kern in (1, 0):
+        g = SC.build_simulation(scene)
+        g.set_option(N.RCS_OPT_STEP_KERNEL, kern)
+        g.set_trace(True)
+        x = scene.xy[bad.astype(np.int64), 0].copy()
+        y = scene.xy[bad.astype(np.int64), 1].copy()
+        x[:200] = np.nan
+        y[100:300] = -np.inf   # (+inf would saturate the insert cell and fail the step: "Index out of bounds")
+        x[300:] = -np.inf
+        g.set_state(bad, x=x, y=y)
+        sims.append(g)
+    for _ in range(2):
+        for g in sims:
+            g.step(R.Duration(*scene.dt))
+        ta, tb = sims[0].read_trace(), sims[1].read_trace()
+        for k in ("id", "nb_offsets", "nb_ids"):
+            assert np.array_equal(ta[k], tb[k]), k
+        for k in ("t_i", "fx", "fy"):
+            assert np.array_equal(ta[k].view(np.uint64), tb[k].view(np.uint64)), k
+        sa, sb = sims[0].read_state(), sims[1].read_state()
+        for k in ("x", "y", "vx", "vy"):
+            assert np.array_equal(np.isnan(sa[k]), np.isnan(sb[k])), k
+            ok = ~np.isnan(sa[k])
+            assert np.array_equal(sa[k][ok].view(np.uint64), sb[k][ok].view(np.uint64)), k
+    sta, stb = sims[0].stats(), sims[1].stats()
+    assert sta.neighbour_total == stb.neighbour_total and sta.candidate_total == stb.candidate_total
+    assert sta.nonfinite_count == stb.nonfinite_count == 400
+
+
 @pytest.mark.parametrize("n_side", [31, 64])
 def test_streaming_kernel_of_no_local_plan_crowds_matches_the_generic_kernel_and_the_oracle(n_side):
     """NoLocalPlan-only crowds take step_stream_kernel (two agents per thread, no index): same bits as the
