@@ -70,6 +70,33 @@ def test_strips_shuffled_crowd_forces_match_single_handle_and_oracle(world):
     assert s["vel_rel_err"] <= P.REL_TOL and s["pos_rel_err"] <= P.REL_TOL
 
 
+@pytest.mark.parametrize("cell,eyesight,s", [(1.0, 2.0, 1.0), (4.0, 2.0, 0.5), (0.5, 1.7, 1.0)])
+def test_strips_with_wide_or_crowded_stencils_match_a_single_handle(cell, eyesight, s):
+    """eyesight > cell (halo reach of several columns) and crowded cells (chunked cooperative kernel) on three
+    ranks: neighbour lists, t_i, forces and state bit-identical to one handle."""
+    rng = np.random.default_rng(23)
+    scene = SC.uniform_crowd(48, "shuffled", s=s, cell=cell, eyesight=eyesight, margin=8.0, seed=5,
+                             lp=("zanlungo", 0.05, 1.0, 0.0, 0.5, 50.0, 0.05))  # heavy agents: the crowd stays sane
+    scene.vxy = scene.vxy + rng.uniform(-0.3, 0.3, size=scene.vxy.shape)
+    single = SC.build_simulation(scene)
+    grp = LocalStripGroup(scene, 3)
+    single.set_trace(True)
+    grp.set_trace(True)
+    dt = R.Duration(0, 10_000_000)
+    finite = 0
+    for _ in range(3):
+        single.step(dt)
+        grp.step(dt)
+        tg, ts = grp.read_trace(), single.read_trace()
+        for k in ("id", "nb_offsets", "nb_ids"):
+            assert np.array_equal(tg[k], ts[k]), k
+        for k in ("t_i", "fx", "fy"):
+            assert np.array_equal(tg[k].view(np.uint64), ts[k].view(np.uint64)), k
+        finite += int(np.isfinite(ts["t_i"]).sum())
+        _same(single.read_state(), grp.read_state())
+    assert finite > 50
+
+
 def test_no_commit_keeps_the_owned_snapshot():
     scene = SC.uniform_crowd(32, "shuffled", margin=8.0, seed=2)
     grp = LocalStripGroup(scene, 3)
