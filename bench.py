@@ -152,10 +152,11 @@ def oracle_run(scene, steps: int, warmup: int):
 
 def cpu_sample_scene(workload: str, variant: str, budget_steps: int):
     """Bounded sample of the workload for the CPU legs: a sub-crowd of the same density, spacing and
-    planner, sized for ~1.7 s/step on one core (the literal data structures cost ~16 us per agent-step)."""
+    planner, sized for ~0.35 s/step on one host core of the GPU box at the default step counts (the literal data
+    structures cost 3-4 us per agent-step there, ~20 us in the build container), i.e. 10-20 s of CPU work per run."""
     from rmf_crowdsim_b200 import scenes as SC
 
-    side = 320 if budget_steps <= 16 else (224 if budget_steps <= 40 else 128)
+    side = 320 if budget_steps <= 40 else (224 if budget_steps <= 120 else 128)
     sc = SC.uniform_crowd(side, variant, margin=64.0)
     return sc, f"{side * side}-agent sub-crowd of {workload} (same density 1/m^2, R=2 m, Zanlungo params), frozen snapshot"
 
@@ -292,7 +293,7 @@ def run_gpu_single(args):
     sample_scene, sample = cpu_sample_scene(workload, args.variant, 6)
     if args.no_local_plan:
         sample_scene.lp = ("none",)
-    cpu_v = None if args.skip_cpu else oracle_run(sample_scene, 5, 1)[0]
+    cpu_v = None if args.skip_cpu else oracle_run(sample_scene, 30, 2)[0]  # ~10 s of CPU work on one core
     line = {
         "metric": "agent-steps/sec (query+Zanlungo+integrate)", "value": value, "unit": "agent-steps/s",
         "n_gpus": 1, "steps": K, "warmup": args.warmup, "ms_per_step": total_ms / K, "higher_is_better": True,
