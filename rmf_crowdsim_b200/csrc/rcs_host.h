@@ -155,6 +155,12 @@ struct rcs_sim {
   void* stage2 = nullptr;
   uint64_t stage2_bytes = 0;
   bool read_inflight = false;
+  // rcs_set_preferred_velocity: upload stream + staging buffer of its own
+  cudaStream_t up_stream = nullptr;
+  cudaEvent_t ev_uploaded = nullptr, ev_pv_scattered = nullptr;
+  void* pv_stage = nullptr;
+  uint64_t pv_stage_bytes = 0;
+  bool pv_inflight = false;
   void* flush_buf = nullptr;
   uint64_t flush_bytes = 0;
   unsigned int* d_bad = nullptr;

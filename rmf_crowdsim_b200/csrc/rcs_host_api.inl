@@ -136,6 +136,13 @@ void rcs_sim_destroy(rcs_sim* s) {
     cudaEventDestroy(s->ev_read_done);
   }
   cudaFree(s->stage2);
+  if (s->up_stream) {
+    cudaStreamSynchronize(s->up_stream);
+    cudaStreamDestroy(s->up_stream);
+    cudaEventDestroy(s->ev_uploaded);
+    cudaEventDestroy(s->ev_pv_scattered);
+  }
+  cudaFree(s->pv_stage);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
@@ -447,29 +454,45 @@ int rcs_set_preferred_velocity(rcs_sim* s, uint64_t m, const uint64_t* ids, cons
     s->err = "ids == NULL requires n == agent count";
     return RCS_ERR_ARG;
   }
+  // The upload runs on its own stream into its own staging buffer, so it overlaps whatever the step stream is still
+  // doing (the previous step, a read-back); only the scatter into the agents' rows is ordered after both.
+  if (!s->up_stream) {
+    CU_TRY(s, cudaStreamCreateWithFlags(&s->up_stream, cudaStreamNonBlocking));
+    CU_TRY(s, cudaEventCreateWithFlags(&s->ev_uploaded, cudaEventDisableTiming));
+    CU_TRY(s, cudaEventCreateWithFlags(&s->ev_pv_scattered, cudaEventDisableTiming));
+  }
+  const uint64_t need = m * (sizeof(uint64_t) + 2 * sizeof(double)) + 256;
+  if (need > s->pv_stage_bytes) {
+    CU_TRY(s, cudaStreamSynchronize(s->up_stream));
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+    cudaFree(s->pv_stage);
+    s->pv_stage = nullptr;
+    s->pv_stage_bytes = 0;
+    CU_TRY(s, cudaMalloc(&s->pv_stage, need + need / 4));
+    s->pv_stage_bytes = need + need / 4;
+    s->pv_inflight = false;
+  }
   rc = build_slot_table(s);
   if (rc) return rc;
-  rc = ensure_stage(s, m * (sizeof(uint64_t) + 2 * sizeof(double)));
-  if (rc) return rc;
-  double* d_val = reinterpret_cast<double*>(static_cast<char*>(s->stage));
+  double2* d_val = static_cast<double2*>(s->pv_stage);
   uint64_t* d_ids = nullptr;
-  CU_TRY(s, cudaMemcpyAsync(d_val, vxy, 2 * m * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  if (s->pv_inflight) CU_TRY(s, cudaStreamWaitEvent(s->up_stream, s->ev_pv_scattered, 0));  // buffer consumed
+  CU_TRY(s, cudaMemcpyAsync(d_val, vxy, 2 * m * sizeof(double), cudaMemcpyHostToDevice, s->up_stream));
   if (ids) {
-    d_ids = reinterpret_cast<uint64_t*>(static_cast<char*>(s->stage) + 2 * m * sizeof(double));
-    CU_TRY(s, cudaMemcpyAsync(d_ids, ids, m * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
+    d_ids = reinterpret_cast<uint64_t*>(static_cast<char*>(s->pv_stage) + 2 * m * sizeof(double));
+    CU_TRY(s, cudaMemcpyAsync(d_ids, ids, m * sizeof(uint64_t), cudaMemcpyHostToDevice, s->up_stream));
   }
+  CU_TRY(s, cudaEventRecord(s->ev_uploaded, s->up_stream));
+  CU_TRY(s, cudaStreamWaitEvent(s->stream, s->ev_uploaded, 0));
   CU_TRY(s, cudaMemsetAsync(s->d_bad, 0, sizeof(unsigned int), s->stream));
   const uint64_t L = std::max<uint64_t>(s->max_id_plus1, 1);
-  scatter_by_id_kernel<double><<<blocks_for(m, 256), 256, 0, s->stream>>>((uint32_t)m, s->order_by_id, d_ids,
-                                                                          s->slot_of_id, L, d_val, 2,
-                                                                          reinterpret_cast<double*>(s->cur.pv), 2,
-                                                                          s->d_bad);
-  scatter_by_id_kernel<double><<<blocks_for(m, 256), 256, 0, s->stream>>>((uint32_t)m, s->order_by_id, d_ids,
-                                                                          s->slot_of_id, L, d_val + 1, 2,
-                                                                          reinterpret_cast<double*>(s->cur.pv) + 1, 2,
-                                                                          s->d_bad);
-  s->launches += 2;
+  scatter_by_id_kernel<double2><<<blocks_for(m, 256), 256, 0, s->stream>>>((uint32_t)m, s->order_by_id, d_ids,
+                                                                           s->slot_of_id, L, d_val, 1, s->cur.pv, 1,
+                                                                           s->d_bad);
+  s->launches += 1;
   CU_TRY(s, cudaGetLastError());
+  CU_TRY(s, cudaEventRecord(s->ev_pv_scattered, s->stream));
+  s->pv_inflight = true;
   if (ids) {
     unsigned int bad = 0;
     CU_TRY(s, cudaMemcpyAsync(&bad, s->d_bad, sizeof(bad), cudaMemcpyDeviceToHost, s->stream));
@@ -479,7 +502,7 @@ int rcs_set_preferred_velocity(rcs_sim* s, uint64_t m, const uint64_t* ids, cons
       return RCS_ERR_ARG;
     }
   }
-  // the stage buffer is reused by later calls on the same stream: stream order keeps this safe
+  // `vxy` (pinned) may be reused once the step stream has passed the scatter: after any rcs_sync / rcs_step / blocking read
   return RCS_OK;
 }
 
@@ -506,14 +529,21 @@ int rcs_read_agents(rcs_sim* s, uint32_t order, uint64_t cap, uint64_t* ids, dou
   // requested order; identity for storage order) into a staging buffer and copied out from there
   rc = ensure_stage(s, (uint64_t)n * 48 + 256);
   if (rc) return rc;
-  const double* posd = reinterpret_cast<const double*>(s->cur.pos);
-  const double* veld = reinterpret_cast<const double*>(s->cur.vel);
   uint64_t off = 0;
   if (ids) { rc = read_array<uint64_t>(s, s->cur.id, 1, ord, n, ids, off); off += (uint64_t)n * 8; if (rc) return rc; }
-  if (x) { rc = read_array<double>(s, posd, 2, ord, n, x, off); off += (uint64_t)n * 8; if (rc) return rc; }
-  if (y) { rc = read_array<double>(s, posd + 1, 2, ord, n, y, off); off += (uint64_t)n * 8; if (rc) return rc; }
-  if (vx) { rc = read_array<double>(s, veld, 2, ord, n, vx, off); off += (uint64_t)n * 8; if (rc) return rc; }
-  if (vy) { rc = read_array<double>(s, veld + 1, 2, ord, n, vy, off); off += (uint64_t)n * 8; if (rc) return rc; }
+  if (x || y || vx || vy) {
+    double* st = reinterpret_cast<double*>(static_cast<char*>(s->stage) + off);
+    double* host[4] = {x, y, vx, vy};
+    double* dev[4];
+    for (int k = 0; k < 4; ++k) dev[k] = host[k] ? st + (uint64_t)k * n : nullptr;
+    gather_state_kernel<<<blocks_for(n, 256), 256, 0, s->stream>>>(n, ord, s->cur.pos, s->cur.vel, dev[0], dev[1],
+                                                                   dev[2], dev[3]);
+    s->launches += 1;
+    for (int k = 0; k < 4; ++k)
+      if (host[k])
+        CU_TRY(s, cudaMemcpyAsync(host[k], dev[k], (uint64_t)n * 8, cudaMemcpyDeviceToHost, s->stream));
+    off += (uint64_t)n * 32;
+  }
   if (next_waypoint) { rc = read_array<uint32_t>(s, s->cur.wp, 1, ord, n, next_waypoint, off); if (rc) return rc; }
   CU_TRY(s, cudaStreamSynchronize(s->stream));
   if (next_waypoint && s->any_route)  // the high half of the word is the route follower's cache entry
@@ -564,24 +594,27 @@ int rcs_read_agents_async(rcs_sim* s, uint32_t order, uint64_t cap, uint64_t* id
   }
   // the previous read's copies must have drained the staging buffer before it is overwritten (device-side wait)
   if (s->read_inflight) CU_TRY(s, cudaStreamWaitEvent(s->stream, s->ev_read_done, 0));
-  struct Item { const void* src; int stride; void* dst; };
-  const double* posd = reinterpret_cast<const double*>(s->cur.pos);
-  const double* veld = reinterpret_cast<const double*>(s->cur.vel);
-  const Item items[5] = {{s->cur.id, 1, ids}, {posd, 2, x}, {posd + 1, 2, y}, {veld, 2, vx}, {veld + 1, 2, vy}};
+  void* host[5] = {ids, x, y, vx, vy};
   char* base = static_cast<char*>(s->stage2);
-  for (int k = 0; k < 5; ++k) {
-    if (!items[k].dst) continue;
+  if (ids) {
     gather_kernel<unsigned long long><<<blocks_for(n, 256), 256, 0, s->stream>>>(
-        n, ord, static_cast<const unsigned long long*>(items[k].src), items[k].stride,
-        reinterpret_cast<unsigned long long*>(base + (uint64_t)k * n * 8));  // 8-byte elements, bit copies
+        n, ord, reinterpret_cast<const unsigned long long*>(s->cur.id), 1, reinterpret_cast<unsigned long long*>(base));
+    s->launches += 1;
+  }
+  if (x || y || vx || vy) {
+    double* dev[4];
+    for (int k = 0; k < 4; ++k)
+      dev[k] = host[k + 1] ? reinterpret_cast<double*>(base + (uint64_t)(k + 1) * n * 8) : nullptr;
+    gather_state_kernel<<<blocks_for(n, 256), 256, 0, s->stream>>>(n, ord, s->cur.pos, s->cur.vel, dev[0], dev[1],
+                                                                   dev[2], dev[3]);
     s->launches += 1;
   }
   CU_TRY(s, cudaGetLastError());
   CU_TRY(s, cudaEventRecord(s->ev_gathered, s->stream));
   CU_TRY(s, cudaStreamWaitEvent(s->copy_stream, s->ev_gathered, 0));
   for (int k = 0; k < 5; ++k)
-    if (items[k].dst)
-      CU_TRY(s, cudaMemcpyAsync(items[k].dst, base + (uint64_t)k * n * 8, (uint64_t)n * 8, cudaMemcpyDeviceToHost,
+    if (host[k])
+      CU_TRY(s, cudaMemcpyAsync(host[k], base + (uint64_t)k * n * 8, (uint64_t)n * 8, cudaMemcpyDeviceToHost,
                                 s->copy_stream));
   CU_TRY(s, cudaEventRecord(s->ev_read_done, s->copy_stream));
   s->read_inflight = true;

@@ -1120,6 +1120,26 @@ __global__ void gather_kernel(uint32_t n, const uint32_t* __restrict__ order, co
   out[k] = src[(size_t)(order ? order[k] : k) * stride];
 }
 
+// x, y, vx, vy of agent order[k] (order == nullptr: identity) into up to four arrays: one 16-byte read per vector
+// instead of one strided 8-byte read per component
+__global__ void gather_state_kernel(uint32_t n, const uint32_t* __restrict__ order, const double2* __restrict__ pos,
+                                    const double2* __restrict__ vel, double* __restrict__ x, double* __restrict__ y,
+                                    double* __restrict__ vx, double* __restrict__ vy) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t i = order ? order[k] : k;
+  if (x || y) {
+    const double2 p = pos[i];
+    if (x) x[k] = p.x;
+    if (y) y[k] = p.y;
+  }
+  if (vx || vy) {
+    const double2 v = vel[i];
+    if (vx) vx[k] = v.x;
+    if (vy) vy[k] = v.y;
+  }
+}
+
 // dst[slot(k)] = src[k] where slot(k) = order[k] (ascending-id addressing) or slot_of_id[ids[k]]
 template <class T>
 __global__ void scatter_by_id_kernel(uint32_t n, const uint32_t* __restrict__ order, const uint64_t* __restrict__ ids,
