@@ -128,7 +128,10 @@ int rcs_remove_agents(rcs_sim* sim, uint64_t n, const uint64_t* ids);
 int rcs_set_state(rcs_sim* sim, uint64_t n, const uint64_t* ids, const double* x, const double* y,
                   const double* vx, const double* vy);
 /* Upload Some(v) results of host-side HighLevelPlanner objects for agents of rcs_hl_host groups.
- * vxy = n interleaved (vx,vy).  ids == NULL: all live agents in ascending-id order. */
+ * vxy = n interleaved (vx,vy).  ids == NULL: all live agents in ascending-id order.
+ * The copy runs on an upload stream of its own, so it overlaps a step that is still in flight; the values take
+ * effect for the next rcs_step*.  A pinned `vxy` (rcs_host_alloc) is read asynchronously: leave it untouched until
+ * the next call that waits for the step stream (rcs_sync, rcs_step, rcs_read_agents). */
 int rcs_set_preferred_velocity(rcs_sim* sim, uint64_t n, const uint64_t* ids, const double* vxy);
 
 #define RCS_ORDER_STORAGE 0u /* device storage order (cell-sorted after a step) */
