@@ -9,6 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import json
 import os
+import sys
 import time
 
 import numpy as np
@@ -208,23 +209,38 @@ def run_e2e(sim, scene, steps: int, warmup: int, dist, torch) -> dict:
     d = Duration(*scene.dt)
     out_n = C.c_uint64()
 
+    split = [0.0, 0.0, 0.0]  # host wall time per call (RCS_E2E_TRACE=1 prints it: where does the host block?)
+
     def one():
         # the download of this step's results runs on a second stream and overlaps the next step's upload + compute
+        ta = time.perf_counter()
         N.check(h, lib.rcs_set_preferred_velocity(h, n, None, pref.ctypes.data_as(N.c_f64p)))
+        tb = time.perf_counter()
         N.check(h, lib.rcs_step_async(h, d.secs, d.nanos, N.RCS_STEP_NO_COMMIT))
+        tc = time.perf_counter()
         N.check(h, lib.rcs_read_agents_async(h, N.RCS_ORDER_ID, n, None, *[o[0].ctypes.data_as(N.c_f64p) for o in outs],
                                              C.byref(out_n)))
+        td = time.perf_counter()
+        split[0] += tb - ta
+        split[1] += tc - tb
+        split[2] += td - tc
 
     for _ in range(warmup):
         one()
     N.check(h, lib.rcs_read_wait(h))
     dist.barrier()
     t0 = time.perf_counter()
+    split[:] = [0.0, 0.0, 0.0]
     for _ in range(steps):
         one()
+    tw = time.perf_counter()
     N.check(h, lib.rcs_read_wait(h))
     dist.barrier()
     t1 = time.perf_counter()
+    if os.environ.get("RCS_E2E_TRACE") and dist.get_rank() == 0:
+        print("e2e host ms/step: set_preferred_velocity %.3f, step_async %.3f, read_agents_async %.3f; final wait %.3f ms; "
+              "total %.3f ms/step" % (1e3 * split[0] / steps, 1e3 * split[1] / steps, 1e3 * split[2] / steps,
+                                      1e3 * (t1 - tw), 1e3 * (t1 - t0) / steps), file=sys.stderr, flush=True)
     t = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     tot = torch.tensor([float(n)], dtype=torch.float64, device="cuda")
