@@ -98,6 +98,8 @@ extern "C" {
     pub fn rcs_step_async(sim: *mut rcs_sim, secs: u64, nanos: u32, flags: u32) -> c_int;
     pub fn rcs_sync(sim: *mut rcs_sim) -> c_int;
     pub fn rcs_step_stats(sim: *mut rcs_sim, out: *mut rcs_stats) -> c_int;
+    pub fn rcs_step_in_loop(sim: *mut rcs_sim, secs: u64, nanos: u32, order: *const u64, n_order: u64,
+                            max_sweeps: u32, out_sweeps: *mut u32) -> c_int;
     pub fn rcs_poll_events(sim: *mut rcs_sim, spawned_cap: u64, spawned_ids: *mut u64, spawned_xy: *mut f64,
                            n_spawned: *mut u64, destroyed_cap: u64, destroyed_ids: *mut u64,
                            n_destroyed: *mut u64) -> c_int;

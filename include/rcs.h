@@ -169,6 +169,16 @@ int rcs_step_async(rcs_sim* sim, uint64_t secs, uint32_t nanos, uint32_t flags);
 int rcs_sync(rcs_sim* sim);
 int rcs_step_stats(rcs_sim* sim, rcs_stats* out);
 
+/* Study mode: one step under the reference's IN-LOOP index semantic -- the index is updated inside
+ * the per-agent loop (lib.rs:299), so agent i finds every agent that came earlier in the iteration order at its NEW
+ * position and every later one at its old position, while the planner is handed their old states (lib.rs:281-286).
+ * `order` = the iteration order as agent ids (the reference's is HashMap-random; ids missing from it come last, by
+ * id); n_order == 0: ascending id.  Computed as a fixed-point iteration of whole-crowd sweeps (rcs_inloop.cuh) that
+ * ends with exactly the sequential loop's result; *out_sweeps = sweeps used, max_sweeps == 0: no limit.
+ * Synchronous; one handle without strips, source sinks or route followers.  Same error behaviour as rcs_step. */
+int rcs_step_in_loop(rcs_sim* sim, uint64_t secs, uint32_t nanos, const uint64_t* order, uint64_t n_order,
+                     uint32_t max_sweeps, uint32_t* out_sweeps);
+
 /* Events for EventListener::{agent_spawned, agent_destroyed} (lib.rs:22-33), accumulated since the
  * last poll, each list in ascending id order per step.  Any pointer may be NULL; counts are always
  * written. */

@@ -107,6 +107,7 @@ SIGNATURES = {
     "rcs_step_async": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32]),
     "rcs_sync": (C.c_int, [C.c_void_p]),
     "rcs_step_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "rcs_step_in_loop": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, c_u64p, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint32)]),
     "rcs_poll_events": (
         C.c_int,
         [C.c_void_p, C.c_uint64, c_u64p, c_f64p, c_u64p, C.c_uint64, c_u64p, c_u64p],

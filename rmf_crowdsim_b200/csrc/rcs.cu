@@ -16,3 +16,4 @@ using namespace rcs_host;
 #include "rcs_host_api.inl"    // create / destroy, planners, agents, the pub `agents` view
 #include "rcs_host_index.inl"  // batched SpatialIndex, trace, options, measurement helpers
 #include "rcs_host_dist.inl"   // spatial strips: NCCL and single-process transports
+#include "rcs_host_inloop.inl" // study mode: the reference's in-loop index semantic as a fixed-point iteration

@@ -17,6 +17,7 @@
 
 #include "rcs_kernels.cuh"
 #include "rcs_step_warp.cuh"
+#include "rcs_inloop.cuh"
 
 namespace rcs_host {
 
@@ -67,6 +68,23 @@ struct NcclApi {
   int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
+
+// buffers of rcs_step_in_loop (allocated on first use)
+struct InLoopMem {
+  double2 *np_a = nullptr, *np_b = nullptr, *nv = nullptr;
+  unsigned long long* rank = nullptr;
+  uint32_t *cellid = nullptr, *perm = nullptr, *cell_count = nullptr, *cell_start = nullptr, *cursor = nullptr;
+  uint32_t* changed = nullptr;
+  uint64_t cap = 0, cells = 0;
+};
+
+inline void inloop_free(InLoopMem*& m) {
+  if (!m) return;
+  cudaFree(m->np_a); cudaFree(m->np_b); cudaFree(m->nv); cudaFree(m->rank); cudaFree(m->cellid); cudaFree(m->perm);
+  cudaFree(m->cell_count); cudaFree(m->cell_start); cudaFree(m->cursor); cudaFree(m->changed);
+  delete m;
+  m = nullptr;
+}
 
 }  // namespace rcs_host
 
@@ -161,6 +179,7 @@ struct rcs_sim {
   void* pv_stage = nullptr;
   uint64_t pv_stage_bytes = 0;
   bool pv_inflight = false;
+  rcs_host::InLoopMem* inloop = nullptr;
   void* flush_buf = nullptr;
   uint64_t flush_bytes = 0;
   unsigned int* d_bad = nullptr;

@@ -143,6 +143,7 @@ void rcs_sim_destroy(rcs_sim* s) {
     cudaEventDestroy(s->ev_pv_scattered);
   }
   cudaFree(s->pv_stage);
+  inloop_free(s->inloop);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }

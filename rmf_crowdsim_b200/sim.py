@@ -408,6 +408,21 @@ class Simulation:
         N.check(self._h, self._lib.rcs_step(self._h, int(dur.secs), int(dur.nanos)))
         self._dispatch_events()
 
+    def step_in_loop(self, dur: Duration, order=None, max_sweeps: int = 0) -> int:
+        """One step under the reference's in-loop index semantic (lib.rs:299) for the iteration order
+        `order` (agent ids; None = ascending id).  Returns the number of whole-crowd sweeps the fixed point took."""
+        if self._host_hl:
+            self._run_host_planners()
+        sweeps = C.c_uint32()
+        if order is None:
+            rc = self._lib.rcs_step_in_loop(self._h, int(dur.secs), int(dur.nanos), None, 0, max_sweeps, C.byref(sweeps))
+        else:
+            order = _u64(order)
+            rc = self._lib.rcs_step_in_loop(self._h, int(dur.secs), int(dur.nanos), _p(order, N.c_u64p), len(order),
+                                            max_sweeps, C.byref(sweeps))
+        N.check(self._h, rc)
+        return int(sweeps.value)
+
     def step_async(self, dur: Duration, no_commit: bool = False) -> None:
         flags = N.RCS_STEP_NO_COMMIT if no_commit else N.RCS_STEP_DEFAULT
         N.check(self._h, self._lib.rcs_step_async(self._h, int(dur.secs), int(dur.nanos), flags))

@@ -1,4 +1,4 @@
-# A/B of library variants: bash gpurun_ab.sh v1 v2 ... (each twice, interleaved)
+# A/B of library variants: bash tools/gpurun/ab.sh v1 v2 ... (each twice, interleaved)
 mkdir -p gpurun_out
 for rep in 1 2; do
 for v in "$@"; do
