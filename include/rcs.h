@@ -268,7 +268,9 @@ int rcs_dist_init(rcs_sim* sim, int32_t rank, int32_t world, const uint8_t nccl_
 /* Column range [c0, c1) owned by `rank` of `world` for this handle's grid. */
 int rcs_dist_strip(rcs_sim* sim, int32_t rank, int32_t world, uint64_t* c0, uint64_t* c1);
 /* add_agents with caller-supplied global ids (the global sequential allocation of lib.rs:128-129
- * is done by the host program across ranks) and initial velocities (vxy may be NULL). */
+ * is done by the host program across ranks) and initial velocities (vxy may be NULL).  Ghosts carry the number of
+ * their (high-level planner, local planner, eyesight) group: EVERY rank makes the same calls in the same order, with
+ * n = 0 where none of the batch lies in its strip, so that the group tables agree. */
 int rcs_dist_add_agents(rcs_sim* sim, uint64_t n, const uint64_t* ids, const double* xy, const double* vxy,
                         uint32_t hl, uint32_t lp, double eyesight);
 /* Single-process transport: sims[r] is rank r of `world` handles that live in this process (on one

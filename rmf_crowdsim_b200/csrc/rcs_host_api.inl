@@ -253,7 +253,12 @@ static int add_agents_impl(rcs_sim* s, uint64_t n, const uint64_t* ids, const do
       }
     }
   }
-  if (n == 0) return RCS_OK;
+  if (n == 0) {
+    // strips: ghosts carry their group number, so every rank must hold the same group table in the same order --
+    // also a rank whose strip is empty at this moment
+    if (s->strip.enabled) find_or_add_group(s, hl, lp, eyesight, source_sink);
+    return RCS_OK;
+  }
   int rc = do_sync(s);
   if (rc) return rc;
   uint32_t grp = find_or_add_group(s, hl, lp, eyesight, source_sink);

@@ -97,6 +97,24 @@ def test_strips_with_wide_or_crowded_stencils_match_a_single_handle(cell, eyesig
     assert finite > 50
 
 
+def test_agents_walk_into_strips_that_started_empty():
+    """The crowd occupies the two middle strips of four; the outer ranks own nothing at first (they still register
+    the crowd's planner group: ghosts carry group numbers), receive their first ghosts after a few steps and adopt
+    the agents that walk in.  Bit-identical to one handle throughout."""
+    scene = SC.uniform_crowd(24, "lane", margin=24.0, seed=17)
+    single = SC.build_simulation(scene)
+    grp = LocalStripGroup(scene, 4)
+    assert grp.agent_counts()[0] == 0 and grp.agent_counts()[3] == 0
+    dt = R.Duration(0, 500_000_000)  # 0.65 m per step
+    for k in range(30):
+        single.step(dt)
+        grp.step(dt)
+        if k % 10 == 9:
+            _same(single.read_state(), grp.read_state())
+    counts = grp.agent_counts()
+    assert counts[0] > 0 and counts[3] > 0 and sum(counts) == scene.n
+
+
 def test_no_commit_keeps_the_owned_snapshot():
     scene = SC.uniform_crowd(32, "shuffled", margin=8.0, seed=2)
     grp = LocalStripGroup(scene, 3)
