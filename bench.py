@@ -426,6 +426,8 @@ def main():
     ap.add_argument("--c5-zanlungo", action="store_true", help="--workload c5 with the Zanlungo planner")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--verify-dist", action="store_true",
+                    help="with --gpus N: committed steps over the NCCL transport compared bit for bit with one handle")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -447,7 +449,10 @@ def main():
     else:
         from rmf_crowdsim_b200 import dist_bench
 
-        dist_bench.run(args)
+        if args.verify_dist:
+            dist_bench.verify(args)
+        else:
+            dist_bench.run(args)
 
 
 if __name__ == "__main__":

@@ -173,6 +173,81 @@ def run(args) -> None:
     dist.destroy_process_group()
 
 
+def verify(args) -> None:
+    """bench.py --gpus N --verify-dist: K COMMITTED steps of the lane-ordered crowd on N ranks over the NCCL
+    transport, then every rank's agents are gathered on rank 0 and compared bit for bit with the same steps on one
+    handle.  (The single-process transport is checked the same way by tests/test_gpu_strips.py; this is the check of
+    the real multi-process exchange: ghosts, redundant ring, migration between processes.)"""
+    import torch
+    import torch.distributed as dist
+
+    from . import sim as S
+    from .strips import StripSimulation, _planners, add_agents_with_ids
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nccl_id = fresh_nccl_id(dist, torch, rank)
+    workload = args.workload or "side512"
+    scene, n_total, ids, xy, vxy = strip_scene(workload, "lane", rank, world, False)
+    per_col = int(round(n_total ** 0.5)) * scene.cell
+    halo_cap = int(3.3 * per_col) + 2048
+    idx = S.LocationHash2D(scene.width, scene.height, scene.cell, scene.offset, capacity=n_total, device=local)
+    sim = StripSimulation(idx, rank, world, nccl_id, halo_capacity=halo_cap)
+    n0 = sim.add_scene_agents(scene, ids, xy, vxy)
+    dt = S.Duration(0, 200_000_000)  # 0.26 m per step: a column boundary is crossed every few steps
+    K = args.steps
+    for _ in range(K):
+        sim.step_async(dt)
+    sim.sync()
+    st = sim.read_state()
+    n1 = len(st["id"])
+    # gather (id, x, y, vx, vy) of every rank on all ranks (padded), as raw 64-bit words
+    counts = torch.zeros(world, dtype=torch.int64, device="cuda")
+    counts[rank] = n1
+    dist.all_reduce(counts)
+    nmax = int(counts.max().item())
+    mine = torch.zeros((5, nmax), dtype=torch.int64, device="cuda")
+    for r, k in enumerate(("id", "x", "y", "vx", "vy")):
+        mine[r, :n1] = torch.from_numpy(st[k].view(np.int64).copy()).cuda()
+    parts = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    ok, detail = True, ""
+    if rank == 0:
+        got = np.concatenate([parts[r][:, : int(counts[r].item())].cpu().numpy() for r in range(world)], axis=1)
+        got = got[:, np.argsort(got[0].view(np.uint64), kind="stable")]
+        full_scene, _, fids, fxy, fvxy = strip_scene(workload, "lane", 0, 1, False)
+        single = S.Simulation(S.LocationHash2D(scene.width, scene.height, scene.cell, scene.offset, capacity=n_total,
+                                               device=local))
+        hl, lp = _planners(full_scene)
+        single._keep = (hl, lp)
+        add_agents_with_ids(single, fids, fxy, fvxy, hl, lp, full_scene.eyesight)
+        for _ in range(K):
+            single.step_async(dt)
+        single.sync()
+        ref = single.read_state()
+        want = np.stack([ref[k].view(np.int64) for k in ("id", "x", "y", "vx", "vy")])
+        ok = got.shape == want.shape and bool(np.array_equal(got, want))
+        if not ok:
+            detail = f"shapes {got.shape} vs {want.shape}"
+            if got.shape == want.shape:
+                bad = np.nonzero((got != want).any(axis=0))[0]
+                detail = f"{len(bad)} agents differ, first id {int(want[0, bad[0]])}"
+        moved = int(abs(n1 - n0))
+        print(json.dumps({"verify_dist": "ok" if ok else "FAILED", "n_gpus": world, "agents": int(n_total), "steps": K,
+                          "transport": "NCCL send/recv between processes", "workload": workload + ", lane-ordered, committed",
+                          "rank0_agents_before_after": [n0, n1], "rank0_net_migration": moved, "detail": detail}),
+              flush=True)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.barrier()
+    dist.destroy_process_group()
+    if not int(flag.item()):
+        raise SystemExit(3)
+
+
 def fresh_nccl_id(dist, torch, rank: int) -> bytes:
     from .strips import nccl_unique_id
 
