@@ -227,7 +227,7 @@ static int sort_into_srt(rcs_sim* s, uint32_t n_ub) {
     sort_big_cells_kernel<<<148, 1024, 0, s->stream>>>(lo, hi, s->cell_start, s->cur.id, s->perm, s->slow_list,
                                                        s->wide_list,
                                                        s->big_list, 4096, s->d_status);
-    gather_sorted_kernel<<<blocks_for(n_ub, 256), 256, 0, s->stream>>>(
+    gather_sorted_kernel<<<blocks_for(n_ub, 128), 128, 0, s->stream>>>(
         n_ub, s->perm, s->cur, s->srt, s->cellid, s->strip.enabled ? s->srt_cell : nullptr, n_sorted_ptr(s),
         s->grid, s->cell_start, s->d_groups, s->d_groups ? s->slices : nullptr, s->d_status);
     s->launches += 4;
