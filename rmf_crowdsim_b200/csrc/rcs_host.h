@@ -171,8 +171,11 @@ struct rcs_sim {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_gathered = nullptr, ev_read_done = nullptr;
   void* stage2 = nullptr;
-  uint64_t stage2_bytes = 0;
+  uint64_t stage2_bytes = 0;  // one half
   bool read_inflight = false;
+  cudaEvent_t ev_half_done[2] = {nullptr, nullptr};
+  bool half_used[2] = {false, false};
+  uint64_t read_seq = 0;
   // rcs_set_preferred_velocity: upload stream + staging buffer of its own
   cudaStream_t up_stream = nullptr;
   cudaEvent_t ev_uploaded = nullptr, ev_pv_scattered = nullptr;

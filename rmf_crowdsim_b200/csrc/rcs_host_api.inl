@@ -134,6 +134,8 @@ void rcs_sim_destroy(rcs_sim* s) {
     cudaStreamDestroy(s->copy_stream);
     cudaEventDestroy(s->ev_gathered);
     cudaEventDestroy(s->ev_read_done);
+    cudaEventDestroy(s->ev_half_done[0]);
+    cudaEventDestroy(s->ev_half_done[1]);
   }
   cudaFree(s->stage2);
   if (s->up_stream) {
@@ -581,7 +583,10 @@ int rcs_read_agents_async(rcs_sim* s, uint32_t order, uint64_t cap, uint64_t* id
     CU_TRY(s, cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
     CU_TRY(s, cudaEventCreateWithFlags(&s->ev_gathered, cudaEventDisableTiming));
     CU_TRY(s, cudaEventCreateWithFlags(&s->ev_read_done, cudaEventDisableTiming));
+    CU_TRY(s, cudaEventCreateWithFlags(&s->ev_half_done[0], cudaEventDisableTiming));
+    CU_TRY(s, cudaEventCreateWithFlags(&s->ev_half_done[1], cudaEventDisableTiming));
   }
+  // two staging halves: the gather of this read runs while the previous read's copies are still draining the other
   const uint64_t need = (uint64_t)n * 40 + 256;
   if (need > s->stage2_bytes) {
     CU_TRY(s, cudaStreamSynchronize(s->copy_stream));
@@ -589,19 +594,22 @@ int rcs_read_agents_async(rcs_sim* s, uint32_t order, uint64_t cap, uint64_t* id
     cudaFree(s->stage2);
     s->stage2 = nullptr;
     s->stage2_bytes = 0;
-    CU_TRY(s, cudaMalloc(&s->stage2, need + need / 4));
-    s->stage2_bytes = need + need / 4;
+    const uint64_t half = (need + need / 4 + 255) & ~255ull;
+    CU_TRY(s, cudaMalloc(&s->stage2, 2 * half));
+    s->stage2_bytes = half;
+    s->half_used[0] = s->half_used[1] = false;
   }
+  const int hb = (int)(s->read_seq++ & 1u);
   const uint32_t* ord = nullptr;
   if (order == RCS_ORDER_ID) {
     rc = build_slot_table(s);
     if (rc) return rc;
     ord = s->order_by_id;
   }
-  // the previous read's copies must have drained the staging buffer before it is overwritten (device-side wait)
-  if (s->read_inflight) CU_TRY(s, cudaStreamWaitEvent(s->stream, s->ev_read_done, 0));
+  // the read before the previous one used this half: its copies must have drained it (device-side wait)
+  if (s->half_used[hb]) CU_TRY(s, cudaStreamWaitEvent(s->stream, s->ev_half_done[hb], 0));
   void* host[5] = {ids, x, y, vx, vy};
-  char* base = static_cast<char*>(s->stage2);
+  char* base = static_cast<char*>(s->stage2) + (uint64_t)hb * s->stage2_bytes;
   if (ids) {
     gather_kernel<unsigned long long><<<blocks_for(n, 256), 256, 0, s->stream>>>(
         n, ord, reinterpret_cast<const unsigned long long*>(s->cur.id), 1, reinterpret_cast<unsigned long long*>(base));
@@ -622,7 +630,9 @@ int rcs_read_agents_async(rcs_sim* s, uint32_t order, uint64_t cap, uint64_t* id
     if (host[k])
       CU_TRY(s, cudaMemcpyAsync(host[k], base + (uint64_t)k * n * 8, (uint64_t)n * 8, cudaMemcpyDeviceToHost,
                                 s->copy_stream));
+  CU_TRY(s, cudaEventRecord(s->ev_half_done[hb], s->copy_stream));
   CU_TRY(s, cudaEventRecord(s->ev_read_done, s->copy_stream));
+  s->half_used[hb] = true;
   s->read_inflight = true;
   return RCS_OK;
 }
