@@ -9,7 +9,7 @@
 //   exchange  NCCL send/recv | peer copies  [strips]
 //   phase B   halo unpack + bin ghosts      [strips]  ghosts appended behind the owned agents
 //             bin -> scan -> scatter -> sort cells by id -> gather      LocationHash2D rebuild (A1, A2)
-//             step_warp (+ step_slow)                 radius query + Zanlungo + Euler (A3-A11), keep flags (A12)
+//             step_warp (+ step_aside)                radius query + Zanlungo + Euler (A3-A11), keep flags (A12)
 //             end_step                                out of bounds / halo / capacity => the step does not stand;
 //                                                     [churn] leaving agents are only FLAGGED (keep = 0): the next
 //                                                     step's counting sort drops them, rcs_sync compacts on demand

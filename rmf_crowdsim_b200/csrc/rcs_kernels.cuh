@@ -23,7 +23,7 @@ struct DevStatus {
   unsigned int capacity_err;    // spawn / ghost append / event buffers ran out of room
   unsigned int spawned;         // agents spawned by source sinks in this step
   unsigned int destroyed;       // agents removed at sinks in this step
-  unsigned int slow_count;      // agents handed to the sequential kernel by the warp-cooperative kernel
+  unsigned int slow_count;      // agents left to the sequential routine (tail of step_aside_kernel)
   unsigned int wide_count;      // agents handed to step_aside_kernel's cooperative part (wide or crowded stencils)
   unsigned int sort_ticket;     // sort_big_cells_kernel: blocks done with a grid-ranked cell (returns to 0)
   unsigned long long first_oob_id;
@@ -536,7 +536,7 @@ struct StepArgs {
   uint32_t* cnt;                   // device counters (CNT_*)
   unsigned long long* ev_destroyed;  // (id, step) pairs of agents removed at sinks
   uint32_t ev_cap;
-  uint32_t* slow_list;             // warp kernel: agents left to the sequential kernel
+  uint32_t* slow_list;             // warp kernel: agents left to the sequential routine
   uint32_t* wide_list;             // warp kernel: agents left to the chunked cooperative routine
   const uint4* slices;             // candidate slices prepared by gather_sorted_kernel (sorted path only)
   const double* routes;            // HL_ROUTE polylines, interleaved x,y
