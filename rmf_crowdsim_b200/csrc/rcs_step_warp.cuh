@@ -372,7 +372,8 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 6) step_warp_kernel(StepArgs a)
     if (zan) {
       // candidate slices of the radius query, prepared by gather_sorted_kernel.  ids >= 2^53 round when they
       // become priorities (zanlungo.rs:94) and groups whose weight-0 pairs cannot be proven zero need the literal
-      // routine for every pair: both are left to the sequential routine, wide or crowded stencils to the chunked cooperative one
+      // routine for every pair: both are left to the sequential routine, wide or crowded stencils to the chunked
+      // cooperative one (step_aside_kernel)
       s0 = sl.x; s1 = sl.y; s2 = sl.z;
       l0 = sl.w & 0xffu; l1 = (sl.w >> 8) & 0xffu; l2 = (sl.w >> 16) & 0xffu;
       const bool coop = g.w0_fast && (me.id >> 53) == 0ull;
