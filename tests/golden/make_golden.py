@@ -12,6 +12,9 @@ Files (all numpy .npz, a few hundred KB in total):
                         512 random (rel_vel, rel_pos) -> time_to_collision (zanlungo.rs:49-74)
   knn_radius_100.npz    the 10 x 10 point grid of location_hash_2d.rs:310-368: kNN and radius answers
   source_sink.npz       tests/event_listeners_test.rs scenario: agent count / spawned / destroyed per step
+  in_loop_400.npz       20 x 20 crowd, ONE step of 0.25 s under the reference's in-loop index update (lib.rs:299) in a
+                        fixed random iteration order: the order, neighbour CSR, t_i, force and output state
+                        (SURVEY.md section 8f-4); differs from the deferred contract for about half of the agents
 """
 import os
 import sys
@@ -127,7 +130,36 @@ def source_sink():
              destroyed=np.array(destroyed), final_id=st["id"], final_x=st["x"])
 
 
+def in_loop_scene():
+    rng = np.random.default_rng(77)
+    scene = SC.uniform_crowd(20, "shuffled", margin=8.0, seed=23, lp=("zanlungo", 0.05, 1.0, 0.0, 0.5, 200.0, 0.1))
+    scene.vxy = scene.vxy + rng.uniform(-0.3, 0.3, size=scene.vxy.shape)
+    order = rng.permutation(scene.n).astype(np.uint64)
+    return scene, order, (0, 250_000_000)
+
+
+def in_loop():
+    scene, order, dt = in_loop_scene()
+    o = O.OracleSim(scene.width, scene.height, scene.cell, scene.offset, index_mode=O.IN_LOOP, iter_order=O.CUSTOM)
+    ids = o.add_agents(scene.xy, o.hl_parity(scene.hl[1]), o.lp_zanlungo(*scene.lp[1:]), scene.eyesight)
+    o.set_state(ids, scene.xy[:, 0], scene.xy[:, 1], scene.vxy[:, 0], scene.vxy[:, 1])
+    o.set_custom_order(order)
+    o.enable_trace(True)
+    o.step(*dt)
+    tr, st = o.read_trace(), o.read_state()
+    d = P.build_oracle(scene)  # the deferred contract on the same input, for the record
+    d.enable_trace(True)
+    d.step(*dt)
+    td = d.read_trace()
+    differs = int(np.sum(np.diff(td["nb_offsets"].astype(np.int64)) != np.diff(tr["nb_offsets"].astype(np.int64))))
+    np.savez(os.path.join(HERE, "in_loop_400.npz"), in_xy=scene.xy, in_vxy=scene.vxy, order=order,
+             dt=np.array(dt, dtype=np.uint64), nb_offsets=tr["nb_offsets"], nb_ids=tr["nb_ids"], t_i=tr["t_i"],
+             fx=tr["fx"], fy=tr["fy"], x=st["x"], y=st["y"], vx=st["vx"], vy=st["vy"],
+             agents_with_other_neighbour_count_than_deferred=np.array([differs]))
+
+
 if __name__ == "__main__":
+    in_loop()
     c1()
     crowd()
     pair_table()
