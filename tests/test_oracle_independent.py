@@ -158,3 +158,109 @@ def test_crowd_step_agrees_with_the_independent_restatement():
         vx, vy = pref[0] + fx * (1.0 / 1.0), pref[1] + fy * (1.0 / 1.0)
         assert _rel(vx, g["vx"][i], 1.0) <= 1e-14 and _rel(vy, g["vy"][i], 1.0) <= 1e-14
     assert finite > 100 and worst <= 1e-13
+
+
+class _Hash2D:
+    """location_hash_2d.rs, second restatement: per-cell id sets (visited in ascending id: the canonical stand-in for
+    the reference's HashSet order), insert cell by truncation (:54-66), query cells by floor (:68-72, :103-122), the
+    width cell count as stride for both coordinates (:59, :74-85)."""
+
+    def __init__(self, width, height, cell, off):
+        self.res, self.off = cell, off
+        self.nx = int(width / cell)
+        self.len = self.nx * int(height / cell)
+        self.cells = {}
+        self.where = {}
+        self.loc = {}
+
+    @staticmethod
+    def _as_usize(v):
+        if v != v or v <= 0.0:
+            return 0
+        return int(v)  # trunc toward zero (values here are far below 2^64)
+
+    def index(self, p):
+        idx = self._as_usize((p[0] - self.off[0]) / self.res) * self.nx + self._as_usize((p[1] - self.off[1]) / self.res)
+        return idx if idx < self.len else None
+
+    def add_or_update(self, i, p):
+        idx = self.index(p)
+        if idx is None:
+            raise ValueError("Index out of bounds")
+        old = self.where.get(i)
+        if old != idx:
+            if old is not None:
+                self.cells[old].discard(i)
+            self.cells.setdefault(idx, set()).add(i)
+            self.where[i] = idx
+        self.loc[i] = p
+
+    def neighbours_in_radius(self, radius, p):
+        fl = lambda v: math.floor(v)  # noqa: E731
+        right = fl(((p[0] + radius) - self.off[0]) / self.res)
+        left = fl(((p[0] - radius) - self.off[0]) / self.res)
+        top = fl(((p[1] + radius) - self.off[1]) / self.res)
+        bottom = fl(((p[1] - radius) - self.off[1]) / self.res)
+        out = []
+        for x in range(left, right + 1):
+            for y in range(bottom, top + 1):
+                if x < 0 or y < 0:
+                    continue
+                idx = x * self.nx + y
+                if idx >= self.len:
+                    continue
+                for j in sorted(self.cells.get(idx, ())):
+                    q = self.loc[j]
+                    if _norm((q[0] - p[0], q[1] - p[1])) < radius:
+                        out.append(j)
+        return out
+
+
+def test_in_loop_step_agrees_with_the_independent_restatement():
+    """lib.rs:259-359 with the index updated INSIDE the loop (:299), written a second time in plain Python: the
+    neighbour set of an agent is decided by the new positions of the agents before it in the iteration order, the
+    planner gets their old states (:281-286).  Against the golden vector the C++ oracle generated in that mode: same
+    neighbour lists, t_i to the bit, forces and new state to the last bits."""
+    g = np.load(os.path.join(G, "in_loop_400.npz"))
+    xy, v, order = g["in_xy"], g["in_vxy"], [int(i) for i in g["order"]]
+    dt = float(int(g["dt"][0])) + float(int(g["dt"][1])) / 1e9
+    z = Zanlungo(0.05, 1.0, 0.0, 0.5, 200.0, 0.1)
+    n = len(xy)
+    side = 20
+    dom = math.ceil((side * 1.0 + 2 * 8.0) / 2.0) * 2.0  # scenes.uniform_crowd(20, margin=8, cell=2)
+    h = _Hash2D(dom, dom, 2.0, (-8.0, -8.0))
+    for i in range(n):
+        h.add_or_update(i, (xy[i, 0], xy[i, 1]))
+    off, nb = g["nb_offsets"].astype(np.int64), g["nb_ids"].astype(np.int64)
+    new_state = {}
+    worst, finite = 0.0, 0
+    for i in order:
+        pref = (-1.3, 0.0) if i % 2 == 0 else (1.3, 0.0)
+        pos_i, vel_i = (xy[i, 0], xy[i, 1]), (v[i, 0], v[i, 1])
+        me = (i, pos_i, vel_i, pref)
+        lst = [j for j in h.neighbours_in_radius(2.0, pos_i) if j != i]
+        assert lst == [int(j) for j in nb[off[i]:off[i + 1]]], i
+        t_i = INF
+        for j in lst:  # OLD states of the neighbours
+            ct = z.time_to_collision((v[j, 0] - vel_i[0], v[j, 1] - vel_i[1]), (xy[j, 0] - pos_i[0], xy[j, 1] - pos_i[1]))
+            if ct < t_i:
+                t_i = ct
+        assert np.float64(t_i).view(np.uint64) == g["t_i"][i].view(np.uint64), i
+        fx = fy = 0.0
+        if t_i != INF:
+            finite += 1
+            for j in lst:
+                f = z.compute_agent_force(me, (j, (xy[j, 0], xy[j, 1]), (v[j, 0], v[j, 1]), (0.0, 0.0)), t_i)
+                fx += f[0]
+                fy += f[1]
+        mag = math.hypot(g["fx"][i], g["fy"][i])
+        worst = max(worst, _rel(fx, g["fx"][i], mag), _rel(fy, g["fy"][i], mag))
+        vel = (pref[0] + fx * (1.0 / 200.0), pref[1] + fy * (1.0 / 200.0))
+        new_pos = (pos_i[0] + vel[0] * dt, pos_i[1] + vel[1] * dt)
+        h.add_or_update(i, new_pos)  # lib.rs:299: the agents after this one see it here
+        new_state[i] = (new_pos, vel)
+    for i in range(n):
+        (px, py), (vx, vy) = new_state[i]
+        assert _rel(px, g["x"][i], 1.0) <= 1e-14 and _rel(py, g["y"][i], 1.0) <= 1e-14
+        assert _rel(vx, g["vx"][i], 1.0) <= 1e-14 and _rel(vy, g["vy"][i], 1.0) <= 1e-14
+    assert finite > 50 and worst <= 1e-13
