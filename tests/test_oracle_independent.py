@@ -264,3 +264,19 @@ def test_in_loop_step_agrees_with_the_independent_restatement():
         assert _rel(px, g["x"][i], 1.0) <= 1e-14 and _rel(py, g["y"][i], 1.0) <= 1e-14
         assert _rel(vx, g["vx"][i], 1.0) <= 1e-14 and _rel(vy, g["vy"][i], 1.0) <= 1e-14
     assert finite > 50 and worst <= 1e-13
+
+
+def test_radius_query_agrees_with_the_independent_hash_grid():
+    """get_neighbours_in_radius (location_hash_2d.rs:240-258) of all 576 agents of the golden crowd step through the
+    second hash-grid restatement: the same lists in the same order (cells x-major then y, ascending id in a cell)."""
+    g = np.load(os.path.join(G, "crowd_576.npz"))
+    xy = g["in_xy"]
+    dom = math.ceil((24 * 1.0 + 2 * 8.0) / 2.0) * 2.0  # scenes.uniform_crowd(24, margin=8, cell=2)
+    h = _Hash2D(dom, dom, 2.0, (-8.0, -8.0))
+    for i in range(len(xy)):
+        h.add_or_update(i, (xy[i, 0], xy[i, 1]))
+        assert h.where[i] == int(g["cells"][i])
+    off, nb = g["nb_offsets"].astype(np.int64), g["nb_ids"].astype(np.int64)
+    for i in range(len(xy)):
+        lst = [j for j in h.neighbours_in_radius(2.0, (xy[i, 0], xy[i, 1])) if j != i]
+        assert lst == [int(j) for j in nb[off[i]:off[i + 1]]], i
