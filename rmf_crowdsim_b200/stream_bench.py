@@ -12,7 +12,6 @@ from __future__ import annotations
 
 import ctypes as C
 import json
-import os
 import time
 
 import numpy as np

@@ -234,8 +234,6 @@ def test_results_do_not_depend_on_insertion_order():
     scene = SC.uniform_crowd(24, "shuffled", margin=8.0, seed=4)
     a = SC.build_simulation(scene)
     # second handle: same ids, storage order reversed, through the explicit-id entry point
-    import ctypes as C
-
     from rmf_crowdsim_b200 import _native as N
 
     b = R.Simulation(R.LocationHash2D(scene.width, scene.height, scene.cell, scene.offset, capacity=scene.n))
