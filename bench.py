@@ -150,6 +150,32 @@ def oracle_run(scene, steps: int, warmup: int):
     return scene.n * steps / total, total
 
 
+def flat_port_run(variant: str, steps: int = 12):
+    """oracle/flat_parallel.cpp on all host cores: NOT the reference (which is single-threaded and HashMap-based) but a
+    strong multi-threaded CPU implementation of the same deferred step (flat arrays, counting-sort grid, the oracle's
+    Zanlungo arithmetic, bit-identical results) -- reported so that the GPU number can also be read against the best
+    the host could do.  Frozen snapshot of a 262,144-agent sub-crowd of the same density."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_ffi as O
+    from rmf_crowdsim_b200 import scenes as SC
+
+    scene = SC.uniform_crowd(512, variant, margin=64.0)
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cols = [np.ascontiguousarray(a) for a in (scene.xy[:, 0], scene.xy[:, 1], scene.vxy[:, 0], scene.vxy[:, 1])]
+    total = 0.0
+    for k in range(steps + 1):
+        work = [c.copy() for c in cols]  # frozen snapshot: every step sees the same crowd (not timed)
+        t0 = time.perf_counter()
+        O.flat_step(scene, *work, scene.dt, threads)
+        t1 = time.perf_counter()
+        if k >= 1:
+            total += t1 - t0
+    return {"value": scene.n * steps / total, "unit": "agent-steps/s", "cores": threads,
+            "kind": "flat-array multi-threaded port, NOT the reference (oracle/flat_parallel.cpp)",
+            "sample": f"{scene.n}-agent sub-crowd (same density 1/m^2, R=2 m, Zanlungo params), frozen snapshot, "
+                      f"{steps} steps"}
+
+
 def cpu_sample_scene(workload: str, variant: str, budget_steps: int):
     """Bounded sample of the workload for the CPU legs: a sub-crowd of the same density, spacing and
     planner, sized for ~0.35 s/step on one host core of the GPU box at the default step counts (the literal data
@@ -294,6 +320,7 @@ def run_gpu_single(args):
     if args.no_local_plan:
         sample_scene.lp = ("none",)
     cpu_v = None if args.skip_cpu else oracle_run(sample_scene, 30, 2)[0]  # ~10 s of CPU work on one core
+    cpu_par = None if (args.skip_cpu or args.no_local_plan) else flat_port_run(args.variant)
     line = {
         "metric": "agent-steps/sec (query+Zanlungo+integrate)", "value": value, "unit": "agent-steps/s",
         "n_gpus": 1, "steps": K, "warmup": args.warmup, "ms_per_step": total_ms / K, "higher_is_better": True,
@@ -307,7 +334,7 @@ def run_gpu_single(args):
             "finite_tti_fraction": st.finite_tti_count / max(n, 1), "nonfinite": int(st.nonfinite_count),
             "oob": int(st.oob_count),
         },
-        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_parallel_port": cpu_par,
         "cpu_baseline": {"value": cpu_v, "unit": "agent-steps/s", "cores": 1, "kind": "port", "sample": sample,
                          "host_cores_available": os.cpu_count()},
         "clocks": clk, "wall_s_timed_region": wall1 - wall0,

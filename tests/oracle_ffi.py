@@ -20,7 +20,7 @@ _lib = None
 
 
 def build() -> None:
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("oracle_capi.cpp", "crowdsim_oracle.hpp", "selftest.cpp")]
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("oracle_capi.cpp", "flat_parallel.cpp", "crowdsim_oracle.hpp", "selftest.cpp")]
     stale = (not os.path.exists(LIB)) or (not os.path.exists(SELFTEST)) or any(
         os.path.getmtime(s) > min(os.path.getmtime(LIB), os.path.getmtime(SELFTEST)) for s in srcs)
     if stale:
@@ -73,6 +73,10 @@ def lib() -> C.CDLL:
         L.orc_ttc.restype = C.c_double
         L.orc_ttc.argtypes = [C.c_double] * 5
         L.orc_agent_force.argtypes = [f64p, C.c_uint64, f64p, C.c_uint64, f64p, C.c_double, f64p]
+        L.orc_flat_step.restype = C.c_int
+        L.orc_flat_step.argtypes = [C.c_uint64, f64p, f64p, f64p, f64p, C.c_double, C.c_double, C.c_double, C.c_double,
+                                    C.c_double, f64p, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint32,
+                                    C.c_int, f64p]
         L.orc_duration_as_secs_f64.restype = C.c_double
         L.orc_duration_as_secs_f64.argtypes = [C.c_uint64, C.c_uint32]
         _lib = L
@@ -232,6 +236,20 @@ class OracleSim:
         out = np.zeros(cap, dtype=np.uint64)
         m = self.L.orc_query_knn(self.h, int(n), float(p[0]), float(p[1]), _p(out, u64p), cap)
         return out[: int(m)].copy()
+
+
+def flat_step(scene, x, y, vx, vy, dt, threads, want_t_i=False):
+    """oracle/flat_parallel.cpp: one deferred step of a single-group parity / Zanlungo crowd on flat arrays with
+    `threads` threads (NOT the reference: a strong CPU implementation for comparison).  Arrays are updated in place."""
+    assert scene.hl[0] == "parity" and scene.lp[0] == "zanlungo"
+    zan = np.ascontiguousarray(scene.lp[1:], dtype=np.float64)
+    t_i = np.zeros(len(x), dtype=np.float64) if want_t_i else None
+    rc = lib().orc_flat_step(len(x), _p(x, f64p), _p(y, f64p), _p(vx, f64p), _p(vy, f64p), scene.width, scene.height,
+                             scene.cell, scene.offset[0], scene.offset[1], _p(zan, f64p), scene.eyesight,
+                             scene.hl[1][0], scene.hl[1][1], int(dt[0]), int(dt[1]), int(threads), _p(t_i, f64p))
+    if rc:
+        raise OracleError(rc, "Index out of bounds")
+    return t_i
 
 
 def ttc(agent_radius, rel_vel, rel_pos) -> float:

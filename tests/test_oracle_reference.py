@@ -122,3 +122,30 @@ def test_width_stride_aliasing():
     o2 = O.OracleSim(8, 4, 1, (0, 0))
     assert o2.cell_of([(4.5, 0.5)])[0] == -1
     assert o2.cell_of([(3.5, 3.5)])[0] == 27
+
+
+def test_flat_parallel_cpu_port_is_bit_identical_to_the_oracle():
+    """oracle/flat_parallel.cpp (the multi-threaded CPU implementation bench.py reports next to the reference-style
+    baseline) against the oracle's deferred mode on a 1 600-agent crowd: t_i and the new state bit for bit, for one
+    thread and for several, over three steps."""
+    import oracle_ffi as O
+    import parity as P
+    from rmf_crowdsim_b200 import scenes as SC
+
+    scene = SC.uniform_crowd(40, "shuffled", margin=16.0, seed=8, lp=("zanlungo", 0.05, 1.0, 0.0, 0.5, 50.0, 0.1))
+    o = P.build_oracle(scene)
+    o.enable_trace(True)
+    st = [{k: np.ascontiguousarray(v.copy()) for k, v in zip(("x", "y", "vx", "vy"),
+                                                              (scene.xy[:, 0], scene.xy[:, 1], scene.vxy[:, 0],
+                                                               scene.vxy[:, 1]))} for _ in range(2)]
+    finite = 0
+    for _ in range(3):
+        o.step(*scene.dt)
+        so, tr = o.read_state(), o.read_trace()
+        for s, threads in zip(st, (1, 5)):
+            t_i = O.flat_step(scene, s["x"], s["y"], s["vx"], s["vy"], scene.dt, threads, want_t_i=True)
+            assert np.array_equal(t_i.view(np.uint64), tr["t_i"].view(np.uint64))
+            for k in ("x", "y", "vx", "vy"):
+                assert np.array_equal(s[k].view(np.uint64), so[k].view(np.uint64)), (k, threads)
+        finite += int(np.isfinite(tr["t_i"]).sum())
+    assert finite > 100
