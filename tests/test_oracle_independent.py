@@ -280,3 +280,56 @@ def test_radius_query_agrees_with_the_independent_hash_grid():
     for i in range(len(xy)):
         lst = [j for j in h.neighbours_in_radius(2.0, (xy[i, 0], xy[i, 1])) if j != i]
         assert lst == [int(j) for j in nb[off[i]:off[i + 1]]], i
+
+
+def _nearest(h, n, p):
+    """get_nearest_neighbours (location_hash_2d.rs:151-238), second restatement: rings of cells around the query cell
+    with HALF-OPEN sides (the (x-s, y-s) corner is visited twice, the (x+s, y+s) corner never), stop at the first ring
+    that brings the candidate count to n or when a whole ring is outside the grid, then a stable sort by distance."""
+    x_idx = math.floor((p[0] - h.off[0]) / h.res)
+    y_idx = math.floor((p[1] - h.off[1]) / h.res)
+    ring = []
+
+    def visit(cx, cy, stat):
+        stat[1] += 1
+        if cx < 0 or cy < 0 or cx * h.nx + cy >= h.len:
+            stat[0] += 1
+            return
+        for j in sorted(h.cells.get(cx * h.nx + cy, ())):
+            ring.append((h.loc[j], j))
+
+    step, all_out = 0, False
+    while len(ring) < n and not all_out:
+        stat = [0, 0]
+        if step == 0:
+            visit(x_idx, y_idx, stat)
+        else:
+            for i in range(x_idx - step, x_idx + step):
+                visit(i, y_idx + step, stat)
+            for i in range(x_idx - step, x_idx + step):
+                visit(i, y_idx - step, stat)
+            for i in range(y_idx - step, y_idx + step):
+                visit(x_idx - step, i, stat)
+            for i in range(y_idx - step, y_idx + step):
+                visit(x_idx + step, i, stat)
+        all_out = stat[0] == stat[1]
+        step += 1
+    ring.sort(key=lambda e: _norm((e[0][0] - p[0], e[0][1] - p[1])))  # list.sort is stable, like the reference's
+    return [j for _, j in ring[:n]]
+
+
+def test_nearest_neighbours_agree_with_the_independent_hash_grid():
+    """The 10 x 10 point grid of the reference's own test (location_hash_2d.rs:310-339) and 61 random queries of the
+    golden vector: the second restatement returns the oracle's lists, duplicates and misses of the ring walk included."""
+    g = np.load(os.path.join(G, "knn_radius_100.npz"))
+    h = _Hash2D(10.0, 10.0, 0.5, (0.0, 0.0))
+    for x in range(10):
+        for y in range(10):
+            h.add_or_update(10 * x + y, (x + 0.5, y + 0.5))
+    assert _nearest(h, 1, (0.6, 0.6)) == [0]                     # the reference's assertions
+    assert _nearest(h, 4, (1.7, 1.6)) == [11, 21, 12, 10]
+    for k, q in enumerate(g["q"]):
+        want = [int(v) for v in g["knn4"][k, : int(g["knn4_count"][k])]]
+        assert _nearest(h, 4, (q[0], q[1])) == want, (k, q)
+        lo, hi = int(g["rad_offsets"][k]), int(g["rad_offsets"][k + 1])
+        assert h.neighbours_in_radius(float(g["radius"][0]), (q[0], q[1])) == [int(v) for v in g["rad_ids"][lo:hi]]
