@@ -333,3 +333,46 @@ def test_nearest_neighbours_agree_with_the_independent_hash_grid():
         assert _nearest(h, 4, (q[0], q[1])) == want, (k, q)
         lo, hi = int(g["rad_offsets"][k]), int(g["rad_offsets"][k + 1])
         assert h.neighbours_in_radius(float(g["radius"][0]), (q[0], q[1])) == [int(v) for v in g["rad_ids"][lo:hi]]
+
+
+def test_source_sink_stream_agrees_with_the_independent_restatement():
+    """lib.rs:195-383 around one SourceSink, written a second time: MonotonicCrowd (source_sink.rs:96-100,
+    round(dt * rate)), the 0.4 m emptiness probe on the start-of-step index (lib.rs:208-217), sequential ids
+    (:128-129), the waypoint test on the OLD position (:305-336) and removal after the commit (:378-380).  Scenario of
+    tests/event_listeners_test.rs; per-step agent count, spawns and despawns and the final state of the golden vector."""
+    g = np.load(os.path.join(G, "source_sink.npz"))
+    h = _Hash2D(1000.0, 1000.0, 20.0, (-500.0, -500.0))
+    source, waypoints, radius_sink, rate, dt = (0.0, 0.0), [(20.0, 0.0)], 1.0, 1.0, 1.0
+    agents, next_id = {}, 0  # id -> [pos, next_waypoint]
+    for step in range(40):
+        spawned = destroyed = 0
+        number = int(math.floor(dt * rate + 0.5))  # f64::round of a positive value
+        if number > 0 and not h.neighbours_in_radius(0.4, source):
+            agents[next_id] = [source, 0]
+            h.add_or_update(next_id, source)
+            next_id += 1
+            spawned = 1
+        updates, leaving = {}, []
+        for i in sorted(agents):
+            pos, wp = agents[i]
+            vel = (1.0, 0.0)  # the stub high-level planner of the test, NoLocalPlan keeps it
+            new_pos = (pos[0] + vel[0] * dt, pos[1] + vel[1] * dt)
+            if _norm((pos[0] - waypoints[wp][0], pos[1] - waypoints[wp][1])) < radius_sink:
+                if wp == len(waypoints) - 1:
+                    leaving.append(i)
+                else:
+                    wp += 1
+            updates[i] = [new_pos, wp]
+        for i, st in updates.items():
+            agents[i] = st
+            h.add_or_update(i, st[0])
+        for i in leaving:
+            del agents[i]
+            h.cells[h.where.pop(i)].discard(i)
+            del h.loc[i]
+            destroyed += 1
+        assert (len(agents), spawned, destroyed) == (int(g["count"][step]), int(g["spawned"][step]),
+                                                      int(g["destroyed"][step])), step
+    ids = sorted(agents)
+    assert ids == [int(v) for v in g["final_id"]]
+    assert [agents[i][0][0] for i in ids] == [float(v) for v in g["final_x"]]
