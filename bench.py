@@ -206,6 +206,8 @@ def run_reference(args):
                          "note": "C++ restatement of the reference CPU path (the Rust reference cannot be built "
                                  "here: no rustc/cargo); single-threaded like the reference"},
         "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        # for context only (the line's value is the reference-style run above): the best this host does on the same step
+        "cpu_parallel_port": flat_port_run(args.variant, 6),
     }
     print(json.dumps(line), flush=True)
 
