@@ -455,6 +455,7 @@ def main():
     ap.add_argument("--c5-zanlungo", action="store_true", help="--workload c5 with the Zanlungo planner")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-verify", action="store_true", help="--gpus N: skip the pre-timing NCCL correctness check")
     ap.add_argument("--verify-dist", action="store_true",
                     help="with --gpus N: committed steps over the NCCL transport compared bit for bit with one handle")
     args = ap.parse_args()

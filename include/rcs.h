@@ -228,7 +228,7 @@ int rcs_read_trace(rcs_sim* sim, uint64_t* ids, double* t_i, double* fx, double*
                    uint64_t* nb_ids);
 
 /* ---- options ------------------------------------------------------------------------------------ */
-#define RCS_OPT_STEP_KERNEL 1u /* 0 = default (warp-cooperative), 1 = thread-per-agent, 2 = warp-cooperative */
+#define RCS_OPT_STEP_KERNEL 1u /* 0 = default (3), 1 = thread-per-agent, 2 = warp-cooperative through L1, 3 = stencil staged in shared memory */
 int rcs_set_option(rcs_sim* sim, uint32_t option, uint64_t value);
 
 /* ---- measurement helpers ---------------------------------------------------------------------- */

@@ -36,6 +36,13 @@ struct Grid {
 
 }  // namespace
 
+namespace {
+int flat_step_impl(uint64_t n, double* x, double* y, double* vx, double* vy, double width, double height, double cell,
+                   double offx, double offy, const double* zan, double eyesight, double hl_vx, double hl_vy,
+                   uint64_t secs, uint32_t nanos, int threads, double* t_i_out, uint32_t* nbc_out, double* fx_out,
+                   double* fy_out, const uint64_t* ids);
+}  // namespace
+
 extern "C" {
 
 // One deferred step of n agents (ids 0..n-1 = array index) with one Zanlungo planner and the parity high-level rule
@@ -44,6 +51,32 @@ extern "C" {
 int orc_flat_step(uint64_t n, double* x, double* y, double* vx, double* vy, double width, double height, double cell,
                   double offx, double offy, const double* zan /*6*/, double eyesight, double hl_vx, double hl_vy,
                   uint64_t secs, uint32_t nanos, int threads, double* t_i_out) {
+  return flat_step_impl(n, x, y, vx, vy, width, height, cell, offx, offy, zan, eyesight, hl_vx, hl_vy, secs, nanos,
+                        threads, t_i_out, nullptr, nullptr, nullptr, nullptr);
+}
+
+// The same step with the per-agent trace the benchmark-size parity tests compare: neighbour-list length (after the
+// self filter, lib.rs:284), t_i and the summed force (zanlungo.rs:208-215).  Any output may be null.  ids (may be
+// null: id = array index) gives the agent ids, strictly ascending, so that a window cut out of a larger crowd keeps
+// its right-of-way priorities (zanlungo.rs:94), its parity rule and its in-cell order.
+int orc_flat_step_trace(uint64_t n, double* x, double* y, double* vx, double* vy, double width, double height,
+                        double cell, double offx, double offy, const double* zan /*6*/, double eyesight, double hl_vx,
+                        double hl_vy, uint64_t secs, uint32_t nanos, int threads, double* t_i_out, uint32_t* nbc_out,
+                        double* fx_out, double* fy_out, const uint64_t* ids) {
+  for (uint64_t i = 1; ids && i < n; ++i)
+    if (ids[i] <= ids[i - 1]) return 2;
+  return flat_step_impl(n, x, y, vx, vy, width, height, cell, offx, offy, zan, eyesight, hl_vx, hl_vy, secs, nanos,
+                        threads, t_i_out, nbc_out, fx_out, fy_out, ids);
+}
+
+}  // extern "C"
+
+namespace {
+
+int flat_step_impl(uint64_t n, double* x, double* y, double* vx, double* vy, double width, double height, double cell,
+                   double offx, double offy, const double* zan, double eyesight, double hl_vx, double hl_vy,
+                   uint64_t secs, uint32_t nanos, int threads, double* t_i_out, uint32_t* nbc_out, double* fx_out,
+                   double* fy_out, const uint64_t* ids) {
   Grid g{cell, offx, offy, f64_as_usize(width / cell), 0};
   g.len = g.nx * f64_as_usize(height / cell);
   const double dt = Duration{secs, nanos}.as_secs_f64();
@@ -72,11 +105,11 @@ int orc_flat_step(uint64_t n, double* x, double* y, double* vx, double* vy, doub
     const uint64_t lo = n * t / threads, hi = n * (t + 1) / threads;
     for (uint64_t i = lo; i < hi; ++i) {
       Agent me;
-      me.agent_id = i;
+      me.agent_id = ids ? ids[i] : i;
       me.position = {x[i], y[i]};
       me.velocity = {vx[i], vy[i]};
       me.eyesight_range = eyesight;
-      const Vec2 pref = (i % 2 == 0) ? Vec2{-hl_vx, -hl_vy} : Vec2{hl_vx, hl_vy};
+      const Vec2 pref = (me.agent_id % 2 == 0) ? Vec2{-hl_vx, -hl_vy} : Vec2{hl_vx, hl_vy};
       me.preferred_vel = pref;  // lib.rs:271
       // get_neighbours_in_radius, location_hash_2d.rs:240-258 (+ self filter lib.rs:284); neighbours keep pref = 0
       nearby.clear();
@@ -92,7 +125,7 @@ int orc_flat_step(uint64_t n, double* x, double* y, double* vx, double* vy, doub
             const Vec2 pj{x[j], y[j]};
             if (norm(pj - me.position) < eyesight && j != i) {
               Agent o;
-              o.agent_id = j;
+              o.agent_id = ids ? ids[j] : j;
               o.position = pj;
               o.velocity = {vx[j], vy[j]};
               nearby.push_back(o);
@@ -102,6 +135,9 @@ int orc_flat_step(uint64_t n, double* x, double* y, double* vx, double* vy, doub
       }
       const Vec2 vel = z.get_desired_velocity(me, nearby, pref);  // zanlungo.rs:201-218
       if (t_i_out) t_i_out[i] = z.last_t_i;
+      if (nbc_out) nbc_out[i] = static_cast<uint32_t>(nearby.size());
+      if (fx_out) fx_out[i] = z.last_force.x;
+      if (fy_out) fy_out[i] = z.last_force.y;
       const Vec2 np = me.position + vel * dt;  // lib.rs:295-297
       uint64_t idx;
       if (!g.insert_cell(np, idx)) oob[t] = 1;  // lib.rs:299-302
@@ -124,4 +160,4 @@ int orc_flat_step(uint64_t n, double* x, double* y, double* vx, double* vy, doub
   return 0;
 }
 
-}  // extern "C"
+}  // namespace

@@ -17,6 +17,7 @@
 
 #include "rcs_kernels.cuh"
 #include "rcs_step_warp.cuh"
+#include "rcs_step_tile.cuh"
 #include "rcs_inloop.cuh"
 
 namespace rcs_host {
@@ -196,6 +197,7 @@ struct rcs_sim {
   rcs_stats stats{};
   cudaEvent_t events[RCS_NUM_EVENTS]{};
   uint32_t opt_step_kernel = 0;
+  bool tile_attr_set = false;
   // dominant-kernel timing
   bool ktiming = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kevents;  // pending pairs

@@ -234,6 +234,10 @@ static int add_agents_impl(rcs_sim* s, uint64_t n, const uint64_t* ids, const do
     return RCS_ERR_ARG;
   }
   CU_TRY(s, cudaSetDevice(s->device));
+  // Steps that are still in flight may have spawned agents (counted on the device only): s->n is exact -- and the
+  // capacity check below meaningful -- only after the sync.
+  int rc = do_sync(s);
+  if (rc) return rc;
   if ((uint64_t)s->n + n > s->cap) {
     s->err = "capacity exceeded";
     return RCS_ERR_CAPACITY;
@@ -261,8 +265,6 @@ static int add_agents_impl(rcs_sim* s, uint64_t n, const uint64_t* ids, const do
     if (s->strip.enabled) find_or_add_group(s, hl, lp, eyesight, source_sink);
     return RCS_OK;
   }
-  int rc = do_sync(s);
-  if (rc) return rc;
   uint32_t grp = find_or_add_group(s, hl, lp, eyesight, source_sink);
   std::vector<double> hv;  // initial velocities: zero unless given (lib.rs:139)
   if (!vxy) hv.assign(2 * n, 0.0);

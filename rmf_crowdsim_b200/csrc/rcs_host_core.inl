@@ -44,11 +44,12 @@ static double radius_threshold(double R) {
 }
 
 static int alloc_agent_arrays(rcs_sim* s, AgentArrays& a, uint64_t cap) {
-  CU_TRY(s, dalloc(&a.pos, cap));
-  CU_TRY(s, dalloc(&a.vel, cap));
-  CU_TRY(s, dalloc(&a.id, cap));
-  CU_TRY(s, dalloc(&a.grp, cap));
-  CU_TRY(s, dalloc(&a.wp, cap));
+  // two spare rows: the bulk-copy staging of step_tile_kernel rounds a row range up to 16 bytes
+  CU_TRY(s, dalloc(&a.pos, cap + 2));
+  CU_TRY(s, dalloc(&a.vel, cap + 2));
+  CU_TRY(s, dalloc(&a.id, cap + 2));
+  CU_TRY(s, dalloc(&a.grp, cap + 2));
+  CU_TRY(s, dalloc(&a.wp, cap + 2));
   a.pv = nullptr;
   return RCS_OK;
 }
@@ -268,7 +269,17 @@ static void launch_step_kernel(rcs_sim* s, const StepArgs& a, uint32_t n_ub, boo
     e1 = kevent_get(s);
     cudaEventRecord(e0, s->stream);
   }
-  if (sorted_input && s->opt_step_kernel != 1) {
+  if (sorted_input && (s->opt_step_kernel == 0 || s->opt_step_kernel == 3)) {
+    // stencil staged in shared memory (rcs_step_tile.cuh); agents it cannot stage go to step_aside_kernel's lists
+    if (!s->tile_attr_set) {  // per device context
+      cudaFuncSetAttribute(step_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared));
+      cudaFuncSetAttribute(step_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      s->tile_attr_set = true;
+    }
+    step_tile_kernel<<<blocks_for(n_ub, 32 * SW_WARPS), 32 * SW_WARPS, sizeof(TileShared), s->stream>>>(a);
+    step_aside_kernel<<<148 * 4, 32 * SW_WARPS, 0, s->stream>>>(a);
+    s->launches += 2;
+  } else if (sorted_input && s->opt_step_kernel != 1) {
     step_warp_kernel<<<blocks_for(n_ub, 32 * SW_WARPS), 32 * SW_WARPS, 0, s->stream>>>(a);
     // the agents it left aside (device-side lists): stencils wider than three columns or crowded columns go to
     // the chunked cooperative kernel, ids >= 2^53 and planners without the weight-0 proof to the sequential one

@@ -280,11 +280,11 @@ int rcs_read_trace(rcs_sim* s, uint64_t* ids, double* t_i, double* fx, double* f
   int rc = trace_host_copy(s, sid, own, hoff);
   if (rc) return rc;
   std::vector<double> hti(n), hfx(n), hfy(n);
-  std::vector<uint64_t> hnb(s->tr_nb_total);
+  std::vector<uint64_t> hnb(nb_ids ? s->tr_nb_total : 0);  // nb_ids == NULL: lengths only (nb_offsets)
   CU_TRY(s, cudaMemcpy(hti.data(), s->tr_ti, n * sizeof(double), cudaMemcpyDeviceToHost));
   CU_TRY(s, cudaMemcpy(hfx.data(), s->tr_fx, n * sizeof(double), cudaMemcpyDeviceToHost));
   CU_TRY(s, cudaMemcpy(hfy.data(), s->tr_fy, n * sizeof(double), cudaMemcpyDeviceToHost));
-  if (s->tr_nb_total)
+  if (nb_ids && s->tr_nb_total)
     CU_TRY(s, cudaMemcpy(hnb.data(), s->tr_nbids, s->tr_nb_total * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   std::vector<uint32_t> order;
   for (uint32_t k = 0; k < n; ++k)
@@ -298,10 +298,9 @@ int rcs_read_trace(rcs_sim* s, uint64_t* ids, double* t_i, double* fx, double* f
     if (fx) fx[r] = hfx[k];
     if (fy) fy[r] = hfy[k];
     if (nb_offsets) nb_offsets[r] = off;
-    for (uint32_t j = hoff[k]; j < hoff[k + 1]; ++j) {
-      if (nb_ids) nb_ids[off] = hnb[j];
-      off++;
-    }
+    if (nb_ids)
+      for (uint32_t j = hoff[k]; j < hoff[k + 1]; ++j) nb_ids[off + (j - hoff[k])] = hnb[j];
+    off += hoff[k + 1] - hoff[k];
   }
   if (nb_offsets) nb_offsets[order.size()] = off;
   return RCS_OK;
@@ -309,7 +308,7 @@ int rcs_read_trace(rcs_sim* s, uint64_t* ids, double* t_i, double* fx, double* f
 
 int rcs_set_option(rcs_sim* s, uint32_t option, uint64_t value) {
   if (!s) return RCS_ERR_ARG;
-  if (option == RCS_OPT_STEP_KERNEL && value <= 2) {
+  if (option == RCS_OPT_STEP_KERNEL && value <= 3) {
     s->opt_step_kernel = (uint32_t)value;
     return RCS_OK;
   }

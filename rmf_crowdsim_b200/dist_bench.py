@@ -24,22 +24,28 @@ def strip_scene(workload: str, variant: str, rank: int, world: int, lp_none: boo
     if side is None and workload.startswith("side"):
         side = int(workload[4:])
     margin = 32.0 if workload == "c2" else 64.0
-    s, cell, speed, seed = 1.0, 2.0, 1.3, 1
+    s, cell, speed, seed, eyesight = 1.0, 2.0, 1.3, 1, 2.0
+    zan = ("zanlungo", 0.05, 1.0, 0.0, 0.5, 1.0, 0.2)
+    if workload.startswith("sparse"):
+        # SURVEY.md 8d "C2-sparse": 5 m spacing, R = cell = 5 m, agent_scale 0.1, force_distance 0.4 -- a crowd whose
+        # force pass is busy and that stays finite for some tens of committed steps
+        side = int(workload[6:])
+        s, cell, eyesight, margin = 5.0, 5.0, 5.0, 40.0
+        zan = ("zanlungo", 0.1, 1.0, 0.0, 0.4, 1.0, 0.2)
     dom = float(np.ceil((side * s + 2 * margin) / cell) * cell)
     ncols = int(dom / cell)
     c0, c1 = ncols * rank // world, ncols * (rank + 1) // world
     # lattice column i sits at x in (i*s, (i+1)*s): cell column floor((x + margin) / cell)
-    i0 = max(0, int(np.floor(c0 * cell - margin)) - 1)
-    i1 = min(side, int(np.ceil(c1 * cell - margin)) + 1)
+    i0 = max(0, int(np.floor((c0 * cell - margin) / s)) - 1)
+    i1 = min(side, int(np.ceil((c1 * cell - margin) / s)) + 1)
     xy = SC.jittered_lattice(side, side, s, seed, i0, i1)
     ids = SC.site_ids(side, side, variant, seed, i0, i1)
     par = (ids % np.uint64(2)).astype(np.float64)
     vxy = np.zeros_like(xy)
     vxy[:, 0] = np.where(par == 0, -speed, speed)
     scene = SC.Scene(name=f"{workload}_{variant}_strip{rank}", width=dom, height=dom, cell=cell,
-                     offset=(-margin, -margin), xy=np.zeros((0, 2)), vxy=np.zeros((0, 2)), eyesight=2.0,
-                     hl=("parity", (speed, 0.0)),
-                     lp=("none",) if lp_none else ("zanlungo", 0.05, 1.0, 0.0, 0.5, 1.0, 0.2), seed=seed)
+                     offset=(-margin, -margin), xy=np.zeros((0, 2)), vxy=np.zeros((0, 2)), eyesight=eyesight,
+                     hl=("parity", (speed, 0.0)), lp=("none",) if lp_none else zan, seed=seed)
     return scene, side * side, ids, xy, vxy
 
 
@@ -56,6 +62,12 @@ def run(args) -> None:
     local = int(os.environ.get("LOCAL_RANK", str(rank)))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # Before anything is timed: the multi-process exchange must reproduce one handle's bits on a crowd whose force pass
+    # is busy and whose agents migrate between the ranks (committed steps).
+    dist_check = None
+    if not getattr(args, "skip_verify", False):
+        w, v, d, k = DIST_VERIFY
+        dist_check = verify_core(dist, torch, rank, world, local, w, v, S.Duration(*d), k)
     nccl_id = fresh_nccl_id(dist, torch, rank)
 
     workload = args.workload or "c4"
@@ -158,6 +170,7 @@ def run(args) -> None:
                 "oob": int(agg[4].item()),
             },
             "e2e": e2e, "gpu_launches": int(agg[6].item()),
+            "dist_verified": None if dist_check is None else dist_check["ok"], "dist_verify": dist_check,
             "roofline": {
                 "bound": "hbm", "kernel": "step_warp_kernel (+ step_aside_kernel) per rank, slowest rank",
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -173,35 +186,26 @@ def run(args) -> None:
     dist.destroy_process_group()
 
 
-def verify(args) -> None:
-    """bench.py --gpus N --verify-dist: K COMMITTED steps of the lane-ordered crowd on N ranks over the NCCL
-    transport, then every rank's agents are gathered on rank 0 and compared bit for bit with the same steps on one
-    handle.  (The single-process transport is checked the same way by tests/test_gpu_strips.py; this is the check of
-    the real multi-process exchange: ghosts, redundant ring, migration between processes.)"""
-    import torch
-    import torch.distributed as dist
-
+def verify_core(dist, torch, rank: int, world: int, local: int, workload: str, variant: str, dt, K: int) -> dict:
+    """K COMMITTED steps of `workload` on `world` ranks over the NCCL transport; every rank's agents are gathered on
+    rank 0 and compared bit for bit (ids, x, y, vx, vy) with the same steps on one handle.  Returns the verdict on
+    every rank.  (The single-process transport is checked the same way by tests/test_gpu_strips.py; this is the
+    check of the real multi-process exchange: ghosts, redundant ring, migration between processes.)"""
     from . import sim as S
     from .strips import StripSimulation, _planners, add_agents_with_ids
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", str(rank)))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nccl_id = fresh_nccl_id(dist, torch, rank)
-    workload = args.workload or "side512"
-    scene, n_total, ids, xy, vxy = strip_scene(workload, "lane", rank, world, False)
-    per_col = int(round(n_total ** 0.5)) * scene.cell
-    halo_cap = int(3.3 * per_col) + 2048
+    scene, n_total, ids, xy, vxy = strip_scene(workload, variant, rank, world, False)
+    per_col = int(round(n_total ** 0.5)) * scene.cell / (5.0 if workload.startswith("sparse") else 1.0)
+    w_cols = 1 + int(np.floor(scene.eyesight / scene.cell)) + 1  # ring + stencil reach
+    halo_cap = int(1.2 * w_cols * per_col) + 2048
     idx = S.LocationHash2D(scene.width, scene.height, scene.cell, scene.offset, capacity=n_total, device=local)
     sim = StripSimulation(idx, rank, world, nccl_id, halo_capacity=halo_cap)
     n0 = sim.add_scene_agents(scene, ids, xy, vxy)
-    dt = S.Duration(0, 200_000_000)  # 0.26 m per step: a column boundary is crossed every few steps
-    K = args.steps
     for _ in range(K):
         sim.step_async(dt)
     sim.sync()
+    stats = sim.stats()
     st = sim.read_state()
     n1 = len(st["id"])
     # gather (id, x, y, vx, vy) of every rank on all ranks (padded), as raw 64-bit words
@@ -214,11 +218,13 @@ def verify(args) -> None:
         mine[r, :n1] = torch.from_numpy(st[k].view(np.int64).copy()).cuda()
     parts = [torch.zeros_like(mine) for _ in range(world)]
     dist.all_gather(parts, mine)
+    mig = torch.tensor([abs(n1 - n0), stats.finite_tti_count], dtype=torch.int64, device="cuda")
+    dist.all_reduce(mig)
     ok, detail = True, ""
     if rank == 0:
         got = np.concatenate([parts[r][:, : int(counts[r].item())].cpu().numpy() for r in range(world)], axis=1)
         got = got[:, np.argsort(got[0].view(np.uint64), kind="stable")]
-        full_scene, _, fids, fxy, fvxy = strip_scene(workload, "lane", 0, 1, False)
+        full_scene, _, fids, fxy, fvxy = strip_scene(workload, variant, 0, 1, False)
         single = S.Simulation(S.LocationHash2D(scene.width, scene.height, scene.cell, scene.offset, capacity=n_total,
                                                device=local))
         hl, lp = _planners(full_scene)
@@ -235,16 +241,46 @@ def verify(args) -> None:
             if got.shape == want.shape:
                 bad = np.nonzero((got != want).any(axis=0))[0]
                 detail = f"{len(bad)} agents differ, first id {int(want[0, bad[0]])}"
-        moved = int(abs(n1 - n0))
-        print(json.dumps({"verify_dist": "ok" if ok else "FAILED", "n_gpus": world, "agents": int(n_total), "steps": K,
-                          "transport": "NCCL send/recv between processes", "workload": workload + ", lane-ordered, committed",
-                          "rank0_agents_before_after": [n0, n1], "rank0_net_migration": moved, "detail": detail}),
-              flush=True)
+        single.spatial_index.close()
+    sim.spatial_index.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
+    return {"ok": bool(int(flag.item())), "n_gpus": world, "agents": int(n_total), "steps": K,
+            "transport": "NCCL send/recv between processes",
+            "workload": f"{workload}, ids {variant}, committed steps of {dt.secs + dt.nanos / 1e9:.4f} s",
+            "net_migration_sum_over_ranks": int(mig[0].item()),
+            "agents_with_finite_t_i_last_step": int(mig[1].item()), "detail": detail}
+
+
+# The force-active crowd of the pre-timing check: 65 536 agents at 5 m spacing, R = cell = 5 m (SURVEY.md 8d
+# "C2-sparse"), 30 committed steps of 1/30 s: ~6 % of the agents run the force pass every step and ~10 000 change
+# their cell column (i.e. migrate when the column is a strip boundary); finite for > 40 steps in the oracle.
+DIST_VERIFY = ("sparse256", "shuffled", (0, 33_333_333), 30)
+
+
+def verify(args) -> None:
+    """bench.py --gpus N --verify-dist: the NCCL transport against one handle, bit for bit: first the lane-ordered
+    crowd (long strides, many migrations, force pass idle), then the force-active sparse crowd."""
+    import torch
+    import torch.distributed as dist
+
+    from . import sim as S
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ok = True
+    for workload, variant, dt, K in ((args.workload or "side512", "lane", (0, 200_000_000), args.steps), DIST_VERIFY):
+        r = verify_core(dist, torch, rank, world, local, workload, variant, S.Duration(*dt), K)
+        ok = ok and r["ok"]
+        if rank == 0:
+            r["verify_dist"] = "ok" if r["ok"] else "FAILED"
+            print(json.dumps(r), flush=True)
     dist.barrier()
     dist.destroy_process_group()
-    if not int(flag.item()):
+    if not ok:
         raise SystemExit(3)
 
 

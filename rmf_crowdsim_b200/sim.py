@@ -307,6 +307,7 @@ class Simulation:
         self._hl_handles: Dict[int, Tuple[HighLevelPlanner, int]] = {}
         self._host_hl: Dict[int, HighLevelPlanner] = {}  # agent id -> host-evaluated planner
         self._host_hl_handle: Optional[int] = None
+        self._host_ss: Dict[Tuple[float, float], SourceSink] = {}  # source position -> sink with a host planner
         self._eyesight: Dict[int, float] = {}
         self._listeners: Dict[int, EventListener] = {}
         self._listener_counter = 0
@@ -375,14 +376,26 @@ class Simulation:
                                 self._hl(source_sink.high_level_planner), self._lp(source_sink.local_planner),
                                 wp.shape[0], _p(wp, N.c_f64p), 1 if source_sink.loop_forever else 0,
                                 float(source_sink.agent_eyesight_range))
+        host_key = None
+        if source_sink.high_level_planner.device_kind is None:
+            # A planner evaluated on the host: its spawned agents are recognised by their spawn position when the
+            # spawn events are dispatched (_dispatch_events), so two such source sinks cannot share a source point.
+            host_key = (float(source_sink.source[0]), float(source_sink.source[1]))
+            if host_key in self._host_ss:
+                raise CrowdsimError(N.RCS_ERR_ARG, "two source sinks with host-evaluated HighLevelPlanners share a "
+                                                   "source position")
         out = C.c_uint64()
         N.check(self._h, self._lib.rcs_add_source_sink(self._h, C.byref(desc), C.byref(out)))
         self._source_sinks[out.value] = source_sink
+        if host_key is not None:
+            self._host_ss[host_key] = source_sink
         return out.value
 
     def remove_source_sink(self, id: int) -> None:
         N.check(self._h, self._lib.rcs_remove_source_sink(self._h, int(id)))
-        self._source_sinks.pop(int(id), None)
+        ss = self._source_sinks.pop(int(id), None)
+        if ss is not None:
+            self._host_ss.pop((float(ss.source[0]), float(ss.source[1])), None)
 
     def add_event_listener(self, event_listener: EventListener) -> int:
         k = self._listener_counter
@@ -459,8 +472,20 @@ class Simulation:
         N.check(self._h, self._lib.rcs_poll_events(self._h, len(sid), _p(sid, N.c_u64p), _p(sxy, N.c_f64p),
                                                    C.byref(ns), len(did), _p(did, N.c_u64p), C.byref(nd)))
         for k in range(ns.value):
+            pos = (float(sxy[2 * k]), float(sxy[2 * k + 1]))
+            ss = self._host_ss.get(pos) if self._host_ss else None
+            if ss is not None:
+                # lib.rs:242-249: set_target(agent, waypoints[0], (radius_sink, radius_sink)) right after the spawn.
+                # The agent was spawned inside the device step with preferred velocity None, so it starts to move
+                # with the NEXT step (the reference moves it in its spawn step already: one step of delay for
+                # host-evaluated planners only).
+                hl = ss.high_level_planner
+                self._host_hl[int(sid[k])] = hl
+                wp0 = ss.waypoints[0]
+                hl.set_target(Agent(int(sid[k]), pos, (0.0, 0.0), 0), (float(wp0[0]), float(wp0[1])),
+                              (float(ss.radius_sink), float(ss.radius_sink)))
             for key in sorted(self._listeners):
-                self._listeners[key].agent_spawned((float(sxy[2 * k]), float(sxy[2 * k + 1])), int(sid[k]))
+                self._listeners[key].agent_spawned(pos, int(sid[k]))
         for k in range(nd.value):
             hl = self._host_hl.pop(int(did[k]), None)
             if hl is not None:
@@ -521,16 +546,20 @@ class Simulation:
     def set_trace(self, on: bool) -> None:
         N.check(self._h, self._lib.rcs_set_trace(self._h, 1 if on else 0))
 
-    def read_trace(self) -> Dict[str, np.ndarray]:
+    def read_trace(self, neighbours: bool = True) -> Dict[str, np.ndarray]:
+        """Trace of the last step in ascending-id order.  neighbours=False skips the neighbour id lists (their
+        lengths are still in nb_offsets): the lists of a 2^24-agent crowd are 1.4 GB."""
         na, nn = C.c_uint64(), C.c_uint64()
         N.check(self._h, self._lib.rcs_trace_sizes(self._h, C.byref(na), C.byref(nn)))
         ids = np.zeros(na.value, dtype=np.uint64)
         ti, fx, fy = (np.zeros(na.value, dtype=np.float64) for _ in range(3))
         off = np.zeros(na.value + 1, dtype=np.uint64)
-        nb = np.zeros(max(nn.value, 1), dtype=np.uint64)
+        nb = np.zeros(max(nn.value, 1) if neighbours else 0, dtype=np.uint64)
         N.check(self._h, self._lib.rcs_read_trace(self._h, _p(ids, N.c_u64p), _p(ti, N.c_f64p), _p(fx, N.c_f64p),
-                                                  _p(fy, N.c_f64p), _p(off, N.c_u64p), _p(nb, N.c_u64p)))
-        return {"id": ids, "t_i": ti, "fx": fx, "fy": fy, "nb_offsets": off, "nb_ids": nb[: nn.value]}
+                                                  _p(fy, N.c_f64p), _p(off, N.c_u64p),
+                                                  _p(nb, N.c_u64p) if neighbours else None))
+        return {"id": ids, "t_i": ti, "fx": fx, "fy": fy, "nb_offsets": off,
+                "nb_ids": nb[: nn.value] if neighbours else None}
 
     def set_option(self, option: int, value: int) -> None:
         N.check(self._h, self._lib.rcs_set_option(self._h, int(option), int(value)))

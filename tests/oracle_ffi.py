@@ -77,6 +77,8 @@ def lib() -> C.CDLL:
         L.orc_flat_step.argtypes = [C.c_uint64, f64p, f64p, f64p, f64p, C.c_double, C.c_double, C.c_double, C.c_double,
                                     C.c_double, f64p, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint32,
                                     C.c_int, f64p]
+        L.orc_flat_step_trace.restype = C.c_int
+        L.orc_flat_step_trace.argtypes = L.orc_flat_step.argtypes + [C.POINTER(C.c_uint32), f64p, f64p, u64p]
         L.orc_duration_as_secs_f64.restype = C.c_double
         L.orc_duration_as_secs_f64.argtypes = [C.c_uint64, C.c_uint32]
         _lib = L
@@ -250,6 +252,26 @@ def flat_step(scene, x, y, vx, vy, dt, threads, want_t_i=False):
     if rc:
         raise OracleError(rc, "Index out of bounds")
     return t_i
+
+
+def flat_step_trace(scene, x, y, vx, vy, dt, threads, ids=None):
+    """flat_step plus the per-agent trace (t_i, neighbour-list length, summed force) in array = id order; the
+    benchmark-size parity tests compare the CUDA path against it (bit-identical to the oracle's deferred mode,
+    tests/test_oracle_reference.py).  ids: the agents' ids (strictly ascending) when the arrays are a window cut out of
+    a larger crowd; None = array index."""
+    assert scene.hl[0] == "parity" and scene.lp[0] == "zanlungo"
+    zan = np.ascontiguousarray(scene.lp[1:], dtype=np.float64)
+    n = len(x)
+    t_i, fx, fy = (np.zeros(n, dtype=np.float64) for _ in range(3))
+    nbc = np.zeros(n, dtype=np.uint32)
+    rc = lib().orc_flat_step_trace(n, _p(x, f64p), _p(y, f64p), _p(vx, f64p), _p(vy, f64p), scene.width, scene.height,
+                                   scene.cell, scene.offset[0], scene.offset[1], _p(zan, f64p), scene.eyesight,
+                                   scene.hl[1][0], scene.hl[1][1], int(dt[0]), int(dt[1]), int(threads), _p(t_i, f64p),
+                                   nbc.ctypes.data_as(C.POINTER(C.c_uint32)), _p(fx, f64p), _p(fy, f64p),
+                                   _p(None if ids is None else np.ascontiguousarray(ids, dtype=np.uint64), u64p))
+    if rc:
+        raise OracleError(rc, "Index out of bounds" if rc == 1 else "ids must be strictly ascending")
+    return {"t_i": t_i, "nbc": nbc, "fx": fx, "fy": fy}
 
 
 def ttc(agent_radius, rel_vel, rel_pos) -> float:

@@ -255,13 +255,14 @@ def test_results_do_not_depend_on_insertion_order():
 
 @pytest.mark.parametrize("variant", ["shuffled", "lane"])
 def test_warp_cooperative_kernel_is_bit_identical_to_thread_per_agent(variant):
-    """The two forms of the hot kernel (rcs_kernels.cuh step_kernel, rcs_step_warp.cuh step_warp_kernel)
-    evaluate the same operations in the same canonical order: every output bit must agree."""
+    """The three forms of the hot kernel (rcs_kernels.cuh step_kernel, rcs_step_warp.cuh step_warp_kernel through
+    L1, rcs_step_tile.cuh step_tile_kernel with the stencil staged in shared memory) evaluate the same operations
+    in the same canonical order: every output bit must agree."""
     from rmf_crowdsim_b200 import _native as N
 
     scene = SC.uniform_crowd(96, variant, margin=16.0, seed=6)
     sims = []
-    for kern in (1, 2):
+    for kern in (1, 2, 3):
         g = SC.build_simulation(scene)
         g.set_option(N.RCS_OPT_STEP_KERNEL, kern)
         g.set_trace(True)
@@ -269,16 +270,18 @@ def test_warp_cooperative_kernel_is_bit_identical_to_thread_per_agent(variant):
     for _ in range(3):
         for g in sims:
             g.step(R.Duration(*scene.dt))
-        ta, tb = sims[0].read_trace(), sims[1].read_trace()
-        for k in ("id", "nb_offsets", "nb_ids"):
-            assert np.array_equal(ta[k], tb[k]), k
-        for k in ("t_i", "fx", "fy"):
-            assert np.array_equal(ta[k].view(np.uint64), tb[k].view(np.uint64)), k
-        sa, sb = sims[0].read_state(), sims[1].read_state()
-        for k in ("x", "y", "vx", "vy"):
-            assert np.array_equal(sa[k].view(np.uint64), sb[k].view(np.uint64)), k
-    assert sims[0].stats().neighbour_total == sims[1].stats().neighbour_total
-    assert sims[0].stats().candidate_total == sims[1].stats().candidate_total
+        ta, sa = sims[0].read_trace(), sims[0].read_state()
+        for other in sims[1:]:
+            tb, sb = other.read_trace(), other.read_state()
+            for k in ("id", "nb_offsets", "nb_ids"):
+                assert np.array_equal(ta[k], tb[k]), k
+            for k in ("t_i", "fx", "fy"):
+                assert np.array_equal(ta[k].view(np.uint64), tb[k].view(np.uint64)), k
+            for k in ("x", "y", "vx", "vy"):
+                assert np.array_equal(sa[k].view(np.uint64), sb[k].view(np.uint64)), k
+    for other in sims[1:]:
+        assert sims[0].stats().neighbour_total == other.stats().neighbour_total
+        assert sims[0].stats().candidate_total == other.stats().candidate_total
 
 
 @pytest.mark.parametrize("cell,eyesight,s", [

@@ -6,6 +6,9 @@ import pytest
 import oracle_ffi as O
 import parity as P
 import rmf_crowdsim_b200 as R
+from rmf_crowdsim_b200 import _native as _N
+
+N_ERR_CAPACITY = _N.RCS_ERR_CAPACITY
 
 pytestmark = pytest.mark.gpu
 
@@ -209,3 +212,57 @@ def test_route_follower_on_the_device_matches_oracle():
     g2.step(R.Duration(1, 0))
     st = g2.read_state()
     assert list(st["x"]) == [2.0, 2.0] and list(st["vx"]) == [1.0, 0.0] and list(st["next_waypoint"]) == [0, 0]
+
+
+def test_source_sink_with_a_host_evaluated_planner_moves_its_agents():
+    """A SourceSink whose HighLevelPlanner is evaluated on the host: spawned agents are registered with the planner
+    (set_target at spawn, lib.rs:242-249) and move from the step after their spawn on; the source is cleared, so the
+    next spawns follow."""
+
+    class East(R.HighLevelPlanner):
+        def __init__(self):
+            self.targets, self.removed = {}, []
+
+        def set_target(self, agent, point, tolerance):
+            self.targets[agent.agent_id] = (point, tolerance)
+
+        def get_desired_velocity(self, agent, time):
+            return (1.0, 0.0) if agent.agent_id in self.targets else None
+
+        def remove_agent_id(self, agent):
+            self.removed.append(agent)
+
+    hl = East()
+    g = R.Simulation(R.LocationHash2D(64.0, 64.0, 2.0, (0.0, 0.0), capacity=256))
+    g.add_source_sink(R.SourceSink((10.0, 10.0), 0.6, R.MonotonicCrowd(1.0), hl, R.NoLocalPlan(), [(14.0, 10.0)], False,
+                                   2.0))
+    with pytest.raises(R.CrowdsimError):
+        g.add_source_sink(R.SourceSink((10.0, 10.0), 0.6, R.MonotonicCrowd(1.0), East(), R.NoLocalPlan(), [(14.0, 10.0)],
+                                       False, 2.0))
+    for _ in range(12):
+        g.step(R.Duration(1, 0))
+    st = g.read_state()
+    assert len(hl.targets) >= 6 and hl.targets[0] == ((14.0, 10.0), (0.6, 0.6))
+    assert hl.removed and hl.removed[0] == 0          # the first agent reached the sink at x = 14
+    assert np.all(st["vx"][:-1] == 1.0) and np.all(np.diff(st["x"]) < 0)  # single file, one metre apart
+
+
+def test_add_agents_after_async_steps_that_spawned_checks_the_real_count():
+    """rcs_add_agents must count the agents that steps still in flight have spawned (they are only known on the
+    device until the sync) before it checks the capacity and picks the insert offset."""
+    cap = 24
+    g = R.Simulation(R.LocationHash2D(64.0, 64.0, 2.0, (0.0, 0.0), capacity=cap))
+    hl, lp = R.ConstantVelocityPlan((1.0, 0.0)), R.NoLocalPlan()
+    g._keep = (hl, lp)
+    g.add_source_sink(R.SourceSink((10.0, 10.0), 0.6, R.MonotonicCrowd(1.0), hl, lp, [(60.0, 10.0)], False, 2.0))
+    for _ in range(20):
+        g.step_async(R.Duration(1, 0))  # 20 spawns, none of them seen by the host yet
+    with pytest.raises(R.CrowdsimError) as e:
+        g.add_agents(np.full((5, 2), 30.0) + np.arange(5)[:, None], hl, lp, 2.0)  # 20 + 5 > 24
+    assert e.value.code == N_ERR_CAPACITY
+    assert g.agent_count() == 20
+    ids = g.add_agents(np.full((4, 2), 30.0) + np.arange(4)[:, None], hl, lp, 2.0)
+    assert list(ids) == [20, 21, 22, 23] and g.agent_count() == 24
+    st = g.read_state()
+    assert np.array_equal(st["id"], np.arange(24, dtype=np.uint64))
+    assert np.array_equal(st["x"][:20], 10.0 + np.arange(20, 0, -1))  # the spawned agents are intact

@@ -149,3 +149,44 @@ def test_flat_parallel_cpu_port_is_bit_identical_to_the_oracle():
                 assert np.array_equal(s[k].view(np.uint64), so[k].view(np.uint64)), (k, threads)
         finite += int(np.isfinite(tr["t_i"]).sum())
     assert finite > 100
+
+
+def test_flat_port_trace_and_windows_with_real_ids():
+    """The trace outputs of oracle/flat_parallel.cpp (what the benchmark-size GPU parity tests compare against): list
+    lengths, t_i and forces equal the oracle's trace bit for bit; and a window cut out of the crowd, stepped with the
+    agents' real ids, reproduces the full crowd's results for every agent whose neighbours are all inside."""
+    import oracle_ffi as O
+    import parity as P
+    from rmf_crowdsim_b200 import scenes as SC
+
+    scene = SC.uniform_crowd(40, "shuffled", margin=16.0, seed=8)
+    o = P.build_oracle(scene)
+    o.enable_trace(True)
+    o.step(*scene.dt)
+    tr, so = o.read_trace(), o.read_state()
+    cols = [np.ascontiguousarray(a.copy()) for a in (scene.xy[:, 0], scene.xy[:, 1], scene.vxy[:, 0], scene.vxy[:, 1])]
+    ft = O.flat_step_trace(scene, *cols, scene.dt, 3)
+    assert np.array_equal(ft["nbc"].astype(np.int64), np.diff(tr["nb_offsets"].astype(np.int64)))
+    for k in ("t_i", "fx", "fy"):
+        assert np.array_equal(ft[k].view(np.uint64), tr[k].view(np.uint64)), k
+    for c, k in zip(cols, ("x", "y", "vx", "vy")):
+        assert np.array_equal(c.view(np.uint64), so[k].view(np.uint64)), k
+    assert np.isfinite(ft["t_i"]).sum() > 100 and np.any(ft["fx"] != 0.0)
+    # window: agents of [10, 30)^2 plus the ring within eyesight + slack, real ids (ascending)
+    x0, y0 = scene.xy[:, 0], scene.xy[:, 1]
+    ring = scene.eyesight + 0.5
+    inner = (x0 >= 10) & (x0 < 30) & (y0 >= 10) & (y0 < 30)
+    outer = (x0 >= 10 - ring) & (x0 < 30 + ring) & (y0 >= 10 - ring) & (y0 < 30 + ring)
+    ids = np.nonzero(outer)[0].astype(np.uint64)
+    wcols = [np.ascontiguousarray(a[outer].copy()) for a in (scene.xy[:, 0], scene.xy[:, 1], scene.vxy[:, 0],
+                                                             scene.vxy[:, 1])]
+    wt = O.flat_step_trace(scene, *wcols, scene.dt, 2, ids=ids)
+    keep = inner[outer]
+    assert keep.sum() > 300
+    for k in ("t_i", "fx", "fy"):
+        assert np.array_equal(wt[k][keep].view(np.uint64), ft[k][inner].view(np.uint64)), k
+    assert np.array_equal(wt["nbc"][keep], ft["nbc"][inner])
+    for c, full in zip(wcols, cols):
+        assert np.array_equal(c[keep].view(np.uint64), full[inner].view(np.uint64))
+    with pytest.raises(O.OracleError):
+        O.flat_step_trace(scene, *wcols, scene.dt, 2, ids=ids[::-1].copy())
