@@ -244,50 +244,10 @@ def run_gpu_single(args):
     state_bytes = n * 48 * 2
     flush = state_bytes < (1 << 30)
 
-    def one_step():
-        N.check(h, lib.rcs_step_async(h, dt.secs, dt.nanos, N.RCS_STEP_NO_COMMIT if frozen else N.RCS_STEP_DEFAULT))
-
     clocks = ClockSampler(0)
-    # warm-up: W steps, then keep stepping for ~0.4 s so the clock samples are taken under load
-    for _ in range(max(args.warmup, 3)):
-        one_step()
-    sim.sync()
-    clocks.start()
-    t_end = time.time() + 0.4
-    heat = 0
-    while time.time() < t_end and heat < 600:  # 600 committed steps = 13 m of the 64 m margin
-        for _ in range(8):
-            one_step()
-        heat += 8
-        sim.sync()
-
-    # timed region: K steps, each bracketed by events on the launching stream, L2 flushed in between
-    launches0 = sim.launch_count()
-    N.check(h, lib.rcs_kernel_timing(h, 1))
-    sim.sync()
-    wall0 = time.perf_counter()
-    total_ms = 0.0
-    K = args.steps
-    done = 0
-    while done < K:
-        batch = min(K - done, N.RCS_NUM_EVENTS // 2)
-        for b in range(batch):
-            if flush:
-                sim.flush_l2(L2_FLUSH_BYTES)
-            sim.event_record(2 * b)
-            one_step()
-            sim.event_record(2 * b + 1)
-        sim.sync()
-        for b in range(batch):
-            total_ms += sim.event_elapsed_ms(2 * b, 2 * b + 1)
-        done += batch
-    wall1 = time.perf_counter()
-    kt_ms, kt_n = C.c_double(), C.c_uint64()
-    N.check(h, lib.rcs_kernel_time_ms(h, C.byref(kt_ms), C.byref(kt_n)))
-    N.check(h, lib.rcs_kernel_timing(h, 0))
-    flush_launches = K if flush else 0
-    launches = sim.launch_count() - launches0 - flush_launches
-    st = sim.stats()
+    m = timed_steps(sim, n, dt, frozen, args.steps, max(args.warmup, 3), flush, heat_s=0.4, clocks=clocks)
+    total_ms, K, kt_ms, kt_n, launches, st = m["total_ms"], args.steps, m["kt_ms"], m["kt_n"], m["launches"], m["stats"]
+    wall0, wall1 = m["wall0"], m["wall1"]
     value = n * K / (total_ms * 1e-3)
 
     # end to end through the C ABI with HOST buffers: every step uploads the preferred velocities of a host
@@ -297,16 +257,12 @@ def run_gpu_single(args):
 
     peaks, how = measured_peaks()
     algo = ALGO_BYTES_NOLOCALPLAN if args.no_local_plan else ALGO_BYTES_ZANLUNGO
-    k_ms = kt_ms.value / max(kt_n.value, 1)
+    k_ms = kt_ms / max(kt_n, 1)
     achieved = algo * n / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
-    if os.path.exists(tp):
-        try:
-            with open(tp) as f:
-                traffic = json.load(f).get(f"{workload}_{args.variant}" + ("_nolp" if args.no_local_plan else ""))
-        except Exception:
-            traffic = None
+    counts0 = kernel_counts(f"{workload}_{args.variant}" + ("_nolp" if args.no_local_plan else ""))
+    if counts0:
+        traffic = counts0.get("kernel_dram_bytes")
     roofline = {
         "bound": "hbm", "kernel": "step_warp_kernel + step_aside_kernel (radius query + Zanlungo + Euler, fused)",
         "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -317,7 +273,20 @@ def run_gpu_single(args):
     fp64 = fp64_info(args)
     if fp64:
         roofline["fp64_peak_tflops_measured"] = fp64
+        counts = kernel_counts(f"{workload}_{args.variant}" + ("_nolp" if args.no_local_plan else ""))
+        if counts and k_ms > 0:
+            # FP64 pipe: double-precision thread instructions per agent (ncu capture of this kernel on this workload,
+            # profiles/kernel_counts.json) x agents / kernel time, against the measured DFMA issue rate
+            peak_inst = fp64["dfma_tflops"] * 1e12 / 2.0
+            dp = counts["dp_inst_per_agent"]
+            roofline["fp64"] = {"dp_inst_per_agent": dp, "peak_dp_inst_per_s": peak_inst,
+                                "achieved_dp_inst_per_s": dp * n / (k_ms * 1e-3),
+                                "frac": dp * n / (k_ms * 1e-3) / peak_inst, "source": counts.get("source")}
+            roofline["step_dram_bytes"] = counts.get("step_dram_bytes")
+            roofline["step_algorithmic_bytes"] = algo * n
 
+    sim.spatial_index.close()
+    secondary = None if args.skip_secondary else secondary_lines(args, scene, peaks)
     sample_scene, sample = cpu_sample_scene(workload, args.variant, 6)
     if args.no_local_plan:
         sample_scene.lp = ("none",)
@@ -336,12 +305,144 @@ def run_gpu_single(args):
             "finite_tti_fraction": st.finite_tti_count / max(n, 1), "nonfinite": int(st.nonfinite_count),
             "oob": int(st.oob_count),
         },
-        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_parallel_port": cpu_par,
+        "e2e": e2e, "gpu_launches": int(launches), "graph_steps_so_far": m["graph_steps"],
+        "roofline": roofline, "cpu_parallel_port": cpu_par,
+        "dist_verified": None, "secondary": secondary,
         "cpu_baseline": {"value": cpu_v, "unit": "agent-steps/s", "cores": 1, "kind": "port", "sample": sample,
                          "host_cores_available": os.cpu_count()},
         "clocks": clk, "wall_s_timed_region": wall1 - wall0,
     }
     print(json.dumps(line), flush=True)
+
+
+def timed_steps(sim, n, dt, frozen, K, warmup, flush, heat_s=0.0, clocks=None):
+    """W untimed steps (+ optional extra load for the clock samples), then K steps, each bracketed by events on the
+    launching stream with L2 flushed in between when the state is small.  Returns times and counters."""
+    import ctypes as C
+
+    from rmf_crowdsim_b200 import _native as N
+
+    lib, h = sim._lib, sim._h
+
+    def one_step():
+        N.check(h, lib.rcs_step_async(h, dt.secs, dt.nanos, N.RCS_STEP_NO_COMMIT if frozen else N.RCS_STEP_DEFAULT))
+
+    for _ in range(warmup):
+        one_step()
+    sim.sync()
+    if clocks is not None:
+        clocks.start()
+    if heat_s > 0:  # keep stepping so that the clock samples are taken under load
+        t_end = time.time() + heat_s
+        heat = 0
+        while time.time() < t_end and heat < 600:  # 600 committed steps = 13 m of the 64 m margin
+            for _ in range(8):
+                one_step()
+            heat += 8
+            sim.sync()
+    launches0 = sim.launch_count()
+    sim.sync()
+    wall0 = time.perf_counter()
+    total_ms = 0.0
+    done = 0
+    while done < K:
+        batch = min(K - done, N.RCS_NUM_EVENTS // 2)
+        for b in range(batch):
+            if flush:
+                sim.flush_l2(L2_FLUSH_BYTES)
+            sim.event_record(2 * b)
+            one_step()
+            sim.event_record(2 * b + 1)
+        sim.sync()
+        for b in range(batch):
+            total_ms += sim.event_elapsed_ms(2 * b, 2 * b + 1)
+        done += batch
+    wall1 = time.perf_counter()
+    launches = sim.launch_count() - launches0 - (K if flush else 0)
+    stats = sim.stats()
+    g0 = sim.graph_stats()
+    # The dominant kernel, bracketed by its own event pair on the launching stream: a second short pass, because a
+    # step with kernel timing on is launched kernel by kernel while the steps above replay as CUDA graphs.
+    N.check(h, lib.rcs_kernel_timing(h, 1))
+    for _ in range(min(K, 10)):
+        if flush:
+            sim.flush_l2(L2_FLUSH_BYTES)
+        one_step()
+    sim.sync()
+    kt_ms, kt_n = C.c_double(), C.c_uint64()
+    N.check(h, lib.rcs_kernel_time_ms(h, C.byref(kt_ms), C.byref(kt_n)))
+    N.check(h, lib.rcs_kernel_timing(h, 0))
+    return {"total_ms": total_ms, "kt_ms": kt_ms.value, "kt_n": kt_n.value, "launches": launches, "stats": stats,
+            "wall0": wall0, "wall1": wall1, "graph_steps": g0[0], "graphs_captured": g0[1]}
+
+
+def secondary_lines(args, main_scene, peaks) -> list:
+    """The rest of BASELINE.md's table in the same run: every entry is a short measurement (3 warm-up + 8 timed
+    steps, CUDA events on the launching stream) of another configuration of BASELINE.json on this GPU."""
+    from rmf_crowdsim_b200 import Duration, _native as N
+    from rmf_crowdsim_b200 import scenes as SC
+
+    out = []
+    K, W = 8, 3
+
+    def entry(name, scene, frozen, lp_none=False):
+        t0 = time.time()
+        e = {"workload": name, "agents": scene.n,
+             "mode": "frozen snapshot (RCS_STEP_NO_COMMIT)" if frozen else "committed steps"}
+        try:
+            sim = SC.build_simulation(scene, device=0)
+            flush = scene.n * 96 < (1 << 30)
+            m = timed_steps(sim, scene.n, Duration(*scene.dt), frozen, K, W, flush)
+            k_ms = m["kt_ms"] / max(m["kt_n"], 1)
+            algo = ALGO_BYTES_NOLOCALPLAN if lp_none else ALGO_BYTES_ZANLUNGO
+            st = m["stats"]
+            e.update({"value": scene.n * K / (m["total_ms"] * 1e-3), "ms_per_step": m["total_ms"] / K, "kernel_ms": k_ms,
+                      "frac": algo * scene.n / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if k_ms > 0 else None,
+                      "frac_whole_step": algo * scene.n * K / (m["total_ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                      "finite_tti_fraction": st.finite_tti_count / max(scene.n, 1), "nonfinite": int(st.nonfinite_count),
+                      "launches_per_step": m["launches"] / K, "steps": K, "graph_steps": m["graph_steps"]})
+            sim.spatial_index.close()
+        except Exception as ex:  # a crowd the model drives out of bounds fails its step: say so, keep going
+            e["error"] = str(ex)
+        e["wall_s"] = round(time.time() - t0, 2)
+        out.append(e)
+
+    entry("C2: 10,000 agents, Zanlungo, ids shuffled", SC.config_c2("shuffled"), True)
+    entry("C3: 2^20 agents, Zanlungo, ids shuffled", SC.config_c3("shuffled"), True)
+    entry("C3: 2^20 agents, NoLocalPlan", SC.config_c3("shuffled", lp=("none",)), True, lp_none=True)
+    if main_scene is not None and main_scene.n == 1 << 24 and main_scene.lp[0] != "none":
+        nolp = main_scene
+        keep_lp = nolp.lp
+        nolp.lp = ("none",)
+        entry("C4: 2^24 agents, NoLocalPlan", nolp, True, lp_none=True)
+        nolp.lp = keep_lp
+    entry("C4: 2^24 agents, Zanlungo, lane-ordered ids (force pass idle)", SC.config_c4("lane"), False)
+    sparse = SC.uniform_crowd(4096, "shuffled", s=5.0, cell=5.0, eyesight=5.0, margin=40.0, seed=1,
+                              lp=("zanlungo", 0.1, 1.0, 0.0, 0.4, 1.0, 0.2), name="sparse_16m")
+    entry("C2-sparse parameters at 2^24 agents (5 m spacing, R = cell = 5 m), Zanlungo, force pass busy", sparse, False)
+    del sparse
+    # C5: SourceSink stream (rmf_crowdsim_b200/stream_bench.py), NoLocalPlan and Zanlungo
+    from rmf_crowdsim_b200 import stream_bench
+
+    for lp_none in (True, False):
+        t0 = time.time()
+        try:
+            out.append(stream_bench.measure(lp_none, K, W, peaks))
+        except Exception as ex:
+            out.append({"workload": "C5 SourceSink stream", "error": str(ex)})
+        out[-1]["wall_s"] = round(time.time() - t0, 2)
+    return out
+
+
+def kernel_counts(key: str):
+    """Per-workload counters taken from the committed ncu captures (profiles/kernel_counts.json, written by
+    tools/ncu_summary.py): DRAM bytes of the dominant kernel and of the whole step, FP64 instructions per agent."""
+    tp = os.path.join(ROOT, "profiles", "kernel_counts.json")
+    try:
+        with open(tp) as f:
+            return json.load(f).get(key)
+    except Exception:
+        return None
 
 
 def fp64_info(args):
@@ -455,6 +556,7 @@ def main():
     ap.add_argument("--c5-zanlungo", action="store_true", help="--workload c5 with the Zanlungo planner")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-secondary", action="store_true", help="skip the other BASELINE configurations")
     ap.add_argument("--skip-verify", action="store_true", help="--gpus N: skip the pre-timing NCCL correctness check")
     ap.add_argument("--verify-dist", action="store_true",
                     help="with --gpus N: committed steps over the NCCL transport compared bit for bit with one handle")

@@ -229,6 +229,13 @@ int rcs_read_trace(rcs_sim* sim, uint64_t* ids, double* t_i, double* fx, double*
 
 /* ---- options ------------------------------------------------------------------------------------ */
 #define RCS_OPT_STEP_KERNEL 1u /* 0 = default (3), 1 = thread-per-agent, 2 = warp-cooperative through L1, 3 = stencil staged in shared memory */
+/* 1 = the step kernel's epilogue files every agent under the cell of the position the next step starts from (cell id +
+ * histogram atomics), so that step's index rebuild starts at the prefix sum.  Off by default: measured slower -- the
+ * atomics cost more inside the latency-bound step kernel than in the bandwidth-bound binning pass they replace. */
+#define RCS_OPT_BIN_AHEAD 2u
+/* 1 (default) = a step whose launch sequence repeats (nothing to upload, no trace, no kernel timing) is captured into a
+ * CUDA graph the second time it comes up and is one graph launch from then on; 0 = always launch kernel by kernel. */
+#define RCS_OPT_GRAPHS 3u
 int rcs_set_option(rcs_sim* sim, uint32_t option, uint64_t value);
 
 /* ---- measurement helpers ---------------------------------------------------------------------- */
@@ -245,8 +252,10 @@ int rcs_flush_l2(rcs_sim* sim, uint64_t bytes);
  * was switched on (it waits for the stream). */
 int rcs_kernel_timing(rcs_sim* sim, int32_t on);
 int rcs_kernel_time_ms(rcs_sim* sim, double* out_ms, uint64_t* out_launches);
-/* Number of kernels launched by this handle so far. */
+/* Number of kernels launched by this handle so far (kernels inside graph launches included). */
 int rcs_launch_count(rcs_sim* sim, uint64_t* out);
+/* Steps that ran as one CUDA graph launch, and graphs captured so far (RCS_OPT_GRAPHS). */
+int rcs_graph_stats(rcs_sim* sim, uint64_t* out_graph_launches, uint64_t* out_captures);
 /* FP64 pipe peak microbenchmark (dependent DFMA chains on all SMs); out_tflops counts FMA = 2. */
 int rcs_fp64_peak(int32_t device, double* out_tflops, double* out_dadd_tops);
 

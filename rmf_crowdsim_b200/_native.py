@@ -33,6 +33,8 @@ RCS_STEP_DEFAULT = 0
 RCS_STEP_NO_COMMIT = 1
 RCS_NUM_EVENTS = 64
 RCS_OPT_STEP_KERNEL = 1
+RCS_OPT_BIN_AHEAD = 2
+RCS_OPT_GRAPHS = 3
 
 
 class SimDesc(C.Structure):
@@ -131,6 +133,7 @@ SIGNATURES = {
     "rcs_kernel_timing": (C.c_int, [C.c_void_p, C.c_int32]),
     "rcs_kernel_time_ms": (C.c_int, [C.c_void_p, c_f64p, c_u64p]),
     "rcs_launch_count": (C.c_int, [C.c_void_p, c_u64p]),
+    "rcs_graph_stats": (C.c_int, [C.c_void_p, c_u64p, c_u64p]),
     "rcs_fp64_peak": (C.c_int, [C.c_int32, c_f64p, c_f64p]),
     "rcs_nccl_unique_id": (C.c_int, [c_u8p]),
     "rcs_dist_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_u8p, C.c_uint64]),

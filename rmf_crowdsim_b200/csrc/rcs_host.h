@@ -70,6 +70,24 @@ struct NcclApi {
   const char* (*GetErrorString)(int) = nullptr;
 };
 
+// A steady-state step as an instantiated CUDA graph (rcs_host_step.inl): everything the launch sequence and the
+// kernel arguments depend on is in the key; the host-side bookkeeping of a step is replayed next to the launch.
+struct StepKey {
+  uint64_t epoch = 0, dt_bits = 0;
+  const void* cur_pos = nullptr;
+  uint32_t flags = 0, n_ub = 0, n = 0;
+  bool cur_has_dead = false, binned_ahead = false;
+  bool operator==(const StepKey& o) const {
+    return epoch == o.epoch && dt_bits == o.dt_bits && cur_pos == o.cur_pos && flags == o.flags && n_ub == o.n_ub &&
+           n == o.n && cur_has_dead == o.cur_has_dead && binned_ahead == o.binned_ahead;
+  }
+};
+struct StepGraph {
+  StepKey key;
+  cudaGraphExec_t exec = nullptr;
+  uint64_t launches = 0;  // kernels in the graph
+};
+
 // buffers of rcs_step_in_loop (allocated on first use)
 struct InLoopMem {
   double2 *np_a = nullptr, *np_b = nullptr, *nv = nullptr;
@@ -97,10 +115,12 @@ struct rcs_sim {
   uint64_t cap = 0;
   uint32_t n = 0;     // live agents owned by this handle, exact as of the last sync
   uint32_t n_ub = 0;  // upper bound used to size launches while steps with churn are in flight
+  uint32_t n_tight = 0, n_coarse = 0xffffffffu;  // source sinks: exact bound / the coarse launch bound made from it
   rcs::AgentArrays cur{}, srt{};
   uint32_t *cellid = nullptr, *perm = nullptr, *cell_count = nullptr, *cell_start = nullptr, *cursor = nullptr;
   uint32_t *tile_sums = nullptr, *scan_total = nullptr, *big_list = nullptr, *slow_list = nullptr, *wide_list = nullptr;
   uint32_t* srt_cell = nullptr;  // strips: insert cell of every sorted agent
+  rcs::TileRange* tile_ranges = nullptr;  // per block of step_tile_kernel: staging ranges (gather_sorted_kernel)
   uint4* slices = nullptr;       // per sorted agent: candidate slices of its radius query (gather_sorted_kernel)
   uint32_t* keep = nullptr;      // churn: 0 = the entry leaves (sink reached, migrated, ghost); dropped by the next sort
   bool cur_has_dead = false;     // `cur` holds entries with keep = 0 (compacted lazily, at rcs_sync)
@@ -130,6 +150,8 @@ struct rcs_sim {
   unsigned long long* d_next_id = nullptr;  // device copy of last_alloc_agent_id (source sinks allocate ids)
   uint64_t max_id_plus1 = 0;
   bool index_valid = false;  // srt + cell_start describe the current positions
+  // the last step's epilogue has binned `cur` for the next one: cellid[] and the histogram cell_count[] are current
+  bool binned_ahead = false;
   // id-addressed access
   uint32_t *slot_of_id = nullptr, *id_rank = nullptr, *order_by_id = nullptr, *presence = nullptr;
   uint64_t slot_table_cap = 0;
@@ -198,6 +220,13 @@ struct rcs_sim {
   cudaEvent_t events[RCS_NUM_EVENTS]{};
   uint32_t opt_step_kernel = 0;
   bool tile_attr_set = false;
+  uint32_t opt_bin_ahead = 0;  // RCS_OPT_BIN_AHEAD
+  // CUDA graphs of steady-state steps
+  uint32_t opt_graphs = 1;     // RCS_OPT_GRAPHS
+  uint64_t graph_epoch = 0;    // bumped by everything that can change a step's launch sequence or kernel arguments
+  std::vector<rcs_host::StepGraph> step_graphs;
+  rcs_host::StepKey recent_keys[2];  // keys of the last steps that ran eagerly (a key seen again is captured)
+  uint64_t graph_launches = 0, graph_captures = 0;
   // dominant-kernel timing
   bool ktiming = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kevents;  // pending pairs

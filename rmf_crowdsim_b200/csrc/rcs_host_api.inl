@@ -82,6 +82,7 @@ int rcs_sim_create(const rcs_sim_desc* desc, rcs_sim** out) {
   CR_TRY(dalloc(&s->wide_list, s->cap + 16));
   CR_TRY(dalloc(&s->keep, s->cap + 16));
   CR_TRY(dalloc(&s->slices, s->cap + 16));
+  CR_TRY(dalloc(&s->tile_ranges, s->cap / GATHER_THREADS + 2));
   CR_TRY(dalloc(&s->cnt, CNT_N));
   CR_TRY(dalloc(&s->d_next_id, 1));
   CR_TRY(cudaMemset(s->cnt, 0, CNT_N * sizeof(uint32_t)));
@@ -108,6 +109,7 @@ void rcs_sim_destroy(rcs_sim* s) {
   if (!s) return;
   cudaSetDevice(s->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
+  step_graphs_clear(s);
   free_agent_arrays(s->cur);
   free_agent_arrays(s->srt);
   cudaFree(s->cellid); cudaFree(s->perm); cudaFree(s->order_by_id); cudaFree(s->cell_count);
@@ -116,7 +118,7 @@ void rcs_sim_destroy(rcs_sim* s) {
   cudaFree(s->d_bad); cudaFree(s->d_bad2); cudaFree(s->slot_of_id); cudaFree(s->id_rank); cudaFree(s->presence);
   cudaFree(s->tr_ti); cudaFree(s->tr_fx); cudaFree(s->tr_fy); cudaFree(s->tr_nbc); cudaFree(s->tr_nbo);
   cudaFree(s->tr_nbids); cudaFree(s->tr_id); cudaFree(s->tr_own); cudaFree(s->stage); cudaFree(s->flush_buf);
-  cudaFree(s->slow_list); cudaFree(s->wide_list); cudaFree(s->keep); cudaFree(s->slices); cudaFree(s->cnt); cudaFree(s->d_next_id); cudaFree(s->srt_cell);
+  cudaFree(s->slow_list); cudaFree(s->wide_list); cudaFree(s->keep); cudaFree(s->slices); cudaFree(s->tile_ranges); cudaFree(s->cnt); cudaFree(s->d_next_id); cudaFree(s->srt_cell);
   cudaFree(s->d_sources); cudaFree(s->d_ss_wp); cudaFree(s->d_blocked); cudaFree(s->d_sg_start);
   cudaFree(s->d_sg_items); cudaFree(s->ev_spawn_id); cudaFree(s->ev_destroyed); cudaFree(s->ev_spawn_xy);
   dist_teardown(s);
@@ -439,6 +441,7 @@ int rcs_set_state(rcs_sim* s, uint64_t m, const uint64_t* ids, const double* x, 
   CU_TRY(s, cudaMemcpyAsync(&bad, s->d_bad, sizeof(bad), cudaMemcpyDeviceToHost, s->stream));
   CU_TRY(s, cudaStreamSynchronize(s->stream));
   s->index_valid = false;
+  s->binned_ahead = false;
   s->tr_valid = false;
   if (bad) {
     s->err = "unknown agent id";

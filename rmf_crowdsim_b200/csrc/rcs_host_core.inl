@@ -80,6 +80,7 @@ static int exclusive_scan(rcs_sim* s, const uint32_t* in, uint64_t len, uint32_t
   }
   uint64_t tiles = (len + SCAN_TILE - 1) / SCAN_TILE;
   if (tiles > s->tile_sums_cap) {
+    s->graph_epoch += 1;
     CU_TRY(s, cudaStreamSynchronize(s->stream));
     cudaFree(s->tile_sums);
     s->tile_sums = nullptr;
@@ -96,6 +97,7 @@ static int exclusive_scan(rcs_sim* s, const uint32_t* in, uint64_t len, uint32_t
 
 static int upload_groups(rcs_sim* s) {
   if (!s->groups_dirty) return RCS_OK;
+  s->graph_epoch += 1;
   if (s->groups.size() > s->d_groups_cap) {
     CU_TRY(s, cudaStreamSynchronize(s->stream));
     cudaFree(s->d_groups);
@@ -152,6 +154,7 @@ static uint32_t find_or_add_group(rcs_sim* s, uint32_t hl, uint32_t lp, double e
 
 static int ensure_pref_arrays(rcs_sim* s) {
   if (s->cur.pv) return RCS_OK;
+  s->graph_epoch += 1;
   CU_TRY(s, cudaStreamSynchronize(s->stream));
   const double nan = std::numeric_limits<double>::quiet_NaN();
   for (AgentArrays* a : {&s->cur, &s->srt}) {
@@ -165,7 +168,9 @@ static int ensure_pref_arrays(rcs_sim* s) {
 }
 
 static void invalidate(rcs_sim* s) {
+  s->graph_epoch += 1;
   s->index_valid = false;
+  s->binned_ahead = false;
   s->slot_valid = false;
   s->tr_valid = false;
 }
@@ -173,6 +178,7 @@ static void invalidate(rcs_sim* s) {
 // The host changed the agent count (add / remove / rollback): rewrite the device counters.
 static int upload_counts(rcs_sim* s) {
   if (!s->cnt_dirty) return RCS_OK;
+  s->graph_epoch += 1;
   set_counts_kernel<<<1, 1, 0, s->stream>>>(s->cnt, s->n);
   s->launches += 1;
   CU_TRY(s, cudaGetLastError());
@@ -182,7 +188,8 @@ static int upload_counts(rcs_sim* s) {
 
 // A1/A2 of SURVEY.md section 8a.  Bins the agents [first, cnt[CNT_TOT]) of `cur` into the histogram
 // (which the caller has zeroed, or which already holds the owned agents of a strip).
-static int bin_agents(rcs_sim* s, uint32_t n_ub, const uint32_t* first, uint32_t launch_n = 0, bool pack = false) {
+static int bin_agents(rcs_sim* s, uint32_t n_ub, const uint32_t* first, uint32_t launch_n = 0, bool pack = false,
+                      bool pack_only = false) {
   if (!n_ub) return RCS_OK;
   if (!launch_n) launch_n = n_ub;  // threads to launch: fewer than n_ub when only the tail behind *first is binned
   PackArgs pk{};
@@ -196,6 +203,12 @@ static int bin_agents(rcs_sim* s, uint32_t n_ub, const uint32_t* first, uint32_t
     pk.left = s->send_l.buf;
     pk.right = s->send_r.buf;
     pk.cur = s->cur;
+  }
+  if (pack_only) {  // the owned agents were binned by the previous step's epilogue
+    halo_pack_kernel<<<blocks_for(launch_n, 256), 256, 0, s->stream>>>(n_ub, s->cnt + CNT_TOT, s->cellid, pk, s->d_status);
+    s->launches += 1;
+    CU_TRY(s, cudaGetLastError());
+    return RCS_OK;
   }
   bin_count_kernel<<<blocks_for(launch_n, 256), 256, 0, s->stream>>>(s->grid, n_ub, first, s->cnt + CNT_TOT, s->cur.pos,
                                                                  s->cur_has_dead ? s->keep : nullptr,
@@ -215,10 +228,14 @@ static int clear_histogram(rcs_sim* s) {
   return RCS_OK;
 }
 
-static int sort_into_srt(rcs_sim* s, uint32_t n_ub) {
+static int sort_into_srt(rcs_sim* s, uint32_t n_ub, bool clear_after_scan = false) {
   const uint64_t lo = s->cell_lo, hi = s->cell_hi, len = hi - lo;
   int rc = exclusive_scan(s, s->cell_count + lo, len, s->cell_start + lo, s->cursor + lo);
   if (rc) return rc;
+  if (clear_after_scan) {  // the step's epilogue refills the histogram for the next step
+    rc = clear_histogram(s);
+    if (rc) return rc;
+  }
   if (n_ub) {
     scatter_perm_kernel<<<blocks_for(n_ub, 256), 256, 0, s->stream>>>(n_ub, s->cnt + CNT_TOT, s->cellid, s->cursor,
                                                                       s->perm, s->d_status);
@@ -228,9 +245,10 @@ static int sort_into_srt(rcs_sim* s, uint32_t n_ub) {
     sort_big_cells_kernel<<<148, 1024, 0, s->stream>>>(lo, hi, s->cell_start, s->cur.id, s->perm, s->slow_list,
                                                        s->wide_list,
                                                        s->big_list, 4096, s->d_status);
-    gather_sorted_kernel<<<blocks_for(n_ub, 128), 128, 0, s->stream>>>(
+    gather_sorted_kernel<<<blocks_for(n_ub, GATHER_THREADS), GATHER_THREADS, 0, s->stream>>>(
         n_ub, s->perm, s->cur, s->srt, s->cellid, s->strip.enabled ? s->srt_cell : nullptr, n_sorted_ptr(s),
-        s->grid, s->cell_start, s->d_groups, s->d_groups ? s->slices : nullptr, s->d_status);
+        s->grid, s->cell_start, s->d_groups, s->d_groups ? s->slices : nullptr,
+        s->d_groups ? s->tile_ranges : nullptr, s->d_status);
     s->launches += 4;
   }
   CU_TRY(s, cudaGetLastError());
@@ -239,6 +257,7 @@ static int sort_into_srt(rcs_sim* s, uint32_t n_ub) {
 
 // (Re)build the canonical (cell, id) sorted copy `srt` of `cur` and cell_start (no step in flight).
 static int build_index(rcs_sim* s) {
+  s->binned_ahead = false;  // the histogram is rebuilt (and consumed) here
   int rc = upload_groups(s);  // gather_sorted_kernel reads the group table
   if (rc) return rc;
   rc = upload_counts(s);
@@ -276,7 +295,7 @@ static void launch_step_kernel(rcs_sim* s, const StepArgs& a, uint32_t n_ub, boo
       cudaFuncSetAttribute(step_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
       s->tile_attr_set = true;
     }
-    step_tile_kernel<<<blocks_for(n_ub, 32 * SW_WARPS), 32 * SW_WARPS, sizeof(TileShared), s->stream>>>(a);
+    step_tile_kernel<<<blocks_for(n_ub, 32 * ST_WARPS), 32 * ST_WARPS, sizeof(TileShared), s->stream>>>(a);
     step_aside_kernel<<<148 * 4, 32 * SW_WARPS, 0, s->stream>>>(a);
     s->launches += 2;
   } else if (sorted_input && s->opt_step_kernel != 1) {
@@ -336,6 +355,7 @@ static int rollback_owned(rcs_sim* s, uint32_t n_tot) {
 // not need this -- the next step's counting sort skips those entries -- so it only runs when the host looks.
 static int compact_cur(rcs_sim* s) {
   if (!s->cur_has_dead) return RCS_OK;
+  s->binned_ahead = false;  // entries move: cellid[] no longer matches
   const uint32_t n_ub = s->n;  // entries in cur, dead ones included
   uint32_t kept = 0;
   if (n_ub) {

@@ -309,7 +309,19 @@ int rcs_read_trace(rcs_sim* s, uint64_t* ids, double* t_i, double* fx, double* f
 int rcs_set_option(rcs_sim* s, uint32_t option, uint64_t value) {
   if (!s) return RCS_ERR_ARG;
   if (option == RCS_OPT_STEP_KERNEL && value <= 3) {
+    s->graph_epoch += 1;
     s->opt_step_kernel = (uint32_t)value;
+    return RCS_OK;
+  }
+  if (option == RCS_OPT_GRAPHS && value <= 1) {
+    s->opt_graphs = (uint32_t)value;
+    s->graph_epoch += 1;
+    return RCS_OK;
+  }
+  if (option == RCS_OPT_BIN_AHEAD && value <= 1) {
+    s->graph_epoch += 1;
+    s->opt_bin_ahead = (uint32_t)value;
+    s->binned_ahead = false;
     return RCS_OK;
   }
   s->err = "unknown option or value";
@@ -382,6 +394,13 @@ int rcs_kernel_time_ms(rcs_sim* s, double* out_ms, uint64_t* out_launches) {
   if (rc) return rc;
   if (out_ms) *out_ms = s->ktime_ms;
   if (out_launches) *out_launches = s->ktime_n;
+  return RCS_OK;
+}
+
+int rcs_graph_stats(rcs_sim* s, uint64_t* out_graph_launches, uint64_t* out_captures) {
+  if (!s) return RCS_ERR_ARG;
+  if (out_graph_launches) *out_graph_launches = s->graph_launches;
+  if (out_captures) *out_captures = s->graph_captures;
   return RCS_OK;
 }
 

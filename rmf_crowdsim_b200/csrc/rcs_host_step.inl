@@ -20,6 +20,7 @@ namespace rcs_host {
 
 static int upload_sources(rcs_sim* s) {
   if (!s->sources_dirty) return RCS_OK;
+  s->graph_epoch += 1;
   CU_TRY(s, cudaStreamSynchronize(s->stream));
   const size_t ns = s->sources.size();
   cudaFree(s->d_sources); cudaFree(s->d_ss_wp); cudaFree(s->d_blocked); cudaFree(s->d_sg_start); cudaFree(s->d_sg_items);
@@ -105,6 +106,13 @@ static StepArgs make_step_args(rcs_sim* s, const AgentArrays& in, const AgentArr
   a.slow_list = s->slow_list;
   a.wide_list = s->wide_list;
   a.slices = full_out ? s->slices : nullptr;
+  a.tile_ranges = full_out ? s->tile_ranges : nullptr;
+  if (full_out && !s->trace && s->opt_bin_ahead) {  // the epilogue bins for the next step
+    a.next_cellid = s->cellid;
+    a.next_count = s->cell_count;
+    a.cell_lo = s->cell_lo;
+    a.cell_hi = s->cell_hi;
+  }
   a.routes = s->d_routes;
   a.route_thr2 = radius_threshold(1e-1);
   if (full_out && churn(s)) {
@@ -128,6 +136,7 @@ static bool sorted_path(const rcs_sim* s) { return s->any_zanlungo || s->any_rou
 // ---- phase A ------------------------------------------------------------------------------------
 static int upload_routes(rcs_sim* s) {
   if (!s->routes_dirty) return RCS_OK;
+  s->graph_epoch += 1;
   CU_TRY(s, cudaStreamSynchronize(s->stream));
   cudaFree(s->d_routes);
   s->d_routes = nullptr;
@@ -135,6 +144,18 @@ static int upload_routes(rcs_sim* s) {
   CU_TRY(s, cudaMemcpy(s->d_routes, s->routes.data(), s->routes.size() * sizeof(double), cudaMemcpyHostToDevice));
   s->routes_dirty = false;
   return RCS_OK;
+}
+
+// Upper bound on the entries of `cur` after this step's spawns (at most one per source, lib.rs:207-219).  The exact
+// bound grows by the number of sources every step; the launch bound derived from it moves in coarse granules, so
+// that consecutive steps launch the same grids (and can replay one CUDA graph).
+static uint32_t spawn_launch_bound(rcs_sim* s) {
+  // n_ub was reset from an exact count (sync, add, remove) -- or happens to equal the last coarse bound
+  if (s->n_ub != s->n_coarse || s->n_tight < s->n) s->n_tight = std::max(s->n_ub, s->n);
+  s->n_tight = (uint32_t)std::min<uint64_t>(s->cap, (uint64_t)s->n_tight + s->n_sources_alive);
+  const uint64_t gran = std::max<uint64_t>(32ull * s->n_sources_alive, 4096);
+  s->n_coarse = (uint32_t)std::min<uint64_t>(s->cap, ((uint64_t)s->n_tight + gran - 1) / gran * gran);
+  return s->n_coarse;
 }
 
 static int step_phase_a(rcs_sim* s, double dt) {
@@ -164,15 +185,19 @@ static int step_phase_a(rcs_sim* s, double dt) {
                                                        s->d_blocked, s->cur, s->keep, (uint32_t)s->cap, s->cnt, s->d_next_id,
                                                        s->ev_spawn_id, s->ev_spawn_xy, s->ev_cap, s->d_status);
     s->launches += 2;
-    s->n_ub = (uint32_t)std::min<uint64_t>(s->cap, (uint64_t)s->n_ub + s->n_sources_alive);
+    s->n_ub = spawn_launch_bound(s);
   }
   if (s->strip.enabled) {
     s->n_ub = (uint32_t)s->cap;
     rc = strip_halo_width(s);  // also narrows [cell_lo, cell_hi) to the strip and its halo
     if (rc) return rc;
-    rc = clear_histogram(s);
-    if (rc) return rc;
-    rc = bin_agents(s, s->n_ub, nullptr, 0, true);  // owned agents: histogram + halo pack in one pass
+    if (s->binned_ahead) {
+      rc = bin_agents(s, s->n_ub, nullptr, 0, true, true);  // binned by the last step's epilogue: halo pack only
+    } else {
+      rc = clear_histogram(s);
+      if (rc) return rc;
+      rc = bin_agents(s, s->n_ub, nullptr, 0, true);  // owned agents: histogram + halo pack in one pass
+    }
     if (rc) return rc;
     if (s->ev_packed) CU_TRY(s, cudaEventRecord(s->ev_packed, s->stream));
   }
@@ -212,13 +237,17 @@ static int step_phase_b(rcs_sim* s, double dt, uint32_t flags) {
           s->cur, s->keep, (uint32_t)s->cap, s->recv_l.buf, s->recv_r.buf, has_l, has_r, s->cnt, s->d_status);
       s->launches += 1;
       rc = bin_agents(s, n_ub, s->cnt + CNT_CUR, ghosts_ub);
-    } else {
+    } else if (!s->binned_ahead) {
       rc = clear_histogram(s);
       if (rc) return rc;
       rc = bin_agents(s, n_ub, nullptr);
+    } else if (s->n_sources_alive) {
+      // binned by the last step's epilogue; only this step's spawns (behind the pre-spawn count) are new
+      rc = bin_agents(s, n_ub, s->cnt + CNT_SAVE, s->n_sources_alive);
     }
     if (rc) return rc;
-    rc = sort_into_srt(s, n_ub);
+    const bool bin_ahead = !s->trace && s->opt_bin_ahead;
+    rc = sort_into_srt(s, n_ub, bin_ahead);
     if (rc) return rc;
     if (s->trace) {
       CU_TRY(s, cudaMemsetAsync(s->tr_nbc, 0, (uint64_t)n_ub * sizeof(uint32_t), s->stream));
@@ -275,6 +304,7 @@ static int step_phase_b(rcs_sim* s, double dt, uint32_t flags) {
   s->launches += 1;
   CU_TRY(s, cudaGetLastError());
   if (churned) s->cur_has_dead = true;
+  s->binned_ahead = n_ub && sorted_path(s) && !s->trace && s->opt_bin_ahead;
   s->pending.push_back(p);
   s->steps_enqueued += 1;
   s->index_valid = false;
@@ -287,7 +317,59 @@ static int step_phase_b(rcs_sim* s, double dt, uint32_t flags) {
 
 extern "C" {
 
+// One step, enqueued kernel by kernel on the handle's stream (which may be capturing).
+static int step_enqueue(rcs_sim* s, double dt, uint32_t flags) {
+  int rc = rcs_host::step_phase_a(s, dt);
+  if (rc) return rc;
+  if (s->strip.enabled) {
+    rc = rcs_host::step_exchange_nccl(s);
+    if (rc) return rc;
+  }
+  return rcs_host::step_phase_b(s, dt, flags);
+}
+
+static void step_graphs_clear(rcs_sim* s) {
+  for (auto& g : s->step_graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  s->step_graphs.clear();
+}
+
+// The host-side half of a step whose device-side half is a graph launch: exactly what step_phase_a / step_phase_b
+// change on the handle in the steady state the key describes (no uploads, no trace, no kernel timing).
+static void step_replay_host(rcs_sim* s, uint32_t flags, uint64_t launches) {
+  using namespace rcs_host;
+  const bool no_commit = (flags & RCS_STEP_NO_COMMIT) != 0;
+  if (s->n_sources_alive) s->n_ub = spawn_launch_bound(s);
+  if (s->strip.enabled) s->n_ub = (uint32_t)s->cap;
+  const uint32_t n_ub = s->n_ub;
+  PendingStep p{s->cur, s->srt, true, s->n};
+  bool churned = false;
+  if (n_ub && sorted_path(s)) {
+    if (churn(s)) {
+      if (no_commit) std::swap(s->cur, s->srt);
+      churned = true;
+    } else if (no_commit) {
+      std::swap(s->cur, s->srt);
+    }
+  } else if (n_ub) {
+    p.snapshot_in_srt = false;
+    if (!no_commit) {
+      std::swap(s->cur.pos, s->srt.pos);
+      std::swap(s->cur.vel, s->srt.vel);
+    }
+  }
+  if (churned) s->cur_has_dead = true;
+  s->binned_ahead = n_ub && sorted_path(s) && s->opt_bin_ahead;
+  s->pending.push_back(p);
+  s->steps_enqueued += 1;
+  s->index_valid = false;
+  s->slot_valid = false;
+  s->tr_valid = false;
+  s->launches += launches;
+}
+
 int rcs_step_async(rcs_sim* s, uint64_t secs, uint32_t nanos, uint32_t flags) {
+  using namespace rcs_host;
   if (!s) return RCS_ERR_ARG;
   CU_TRY(s, cudaSetDevice(s->device));
   if (!s->local_group.empty()) {
@@ -295,13 +377,66 @@ int rcs_step_async(rcs_sim* s, uint64_t secs, uint32_t nanos, uint32_t flags) {
     return RCS_ERR_ARG;
   }
   const double dt = (double)secs + (double)nanos / 1000000000.0;  // Duration::as_secs_f64
-  int rc = step_phase_a(s, dt);
-  if (rc) return rc;
-  if (s->strip.enabled) {
-    rc = step_exchange_nccl(s);
-    if (rc) return rc;
+  // A step in the steady state -- nothing to upload, no trace, no kernel timing -- launches the same kernels with the
+  // same arguments as the last step with the same key did: the second time a key comes up the step is captured into
+  // a CUDA graph, from then on it is one graph launch (a 10 000-agent step is a dozen kernels of a few microseconds,
+  // the launch gaps between them are most of its time; the same holds for a rank of an 8-GPU run).
+  const bool steady = s->opt_graphs && !s->trace && !s->ktiming && !s->groups_dirty && !s->routes_dirty &&
+                      !s->sources_dirty && !s->cnt_dirty && s->pending.size() < 4096;
+  StepKey key;
+  if (steady) {
+    key.epoch = s->graph_epoch;
+    std::memcpy(&key.dt_bits, &dt, sizeof(double));
+    key.cur_pos = s->cur.pos;
+    key.flags = flags;
+    key.n_ub = s->n_ub;
+    key.n = s->n;
+    key.cur_has_dead = s->cur_has_dead;
+    key.binned_ahead = s->binned_ahead;
+    if (!s->step_graphs.empty() && s->step_graphs.front().key.epoch != key.epoch) step_graphs_clear(s);
+    for (const StepGraph& g : s->step_graphs) {
+      if (g.key == key) {
+        CU_TRY(s, cudaGraphLaunch(g.exec, s->stream));
+        step_replay_host(s, flags, g.launches);
+        s->graph_launches += 1;
+        return RCS_OK;
+      }
+    }
+    if ((s->recent_keys[0] == key || s->recent_keys[1] == key) && s->step_graphs.size() < 8) {
+      const uint64_t launches0 = s->launches;
+      CU_TRY(s, cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+      int rc = step_enqueue(s, dt, flags);
+      cudaGraph_t graph = nullptr;
+      cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+      if (rc) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+      }
+      if (e != cudaSuccess || !graph) {
+        s->err = std::string("CUDA error: ") + cudaGetErrorString(e) + " at cudaStreamEndCapture";
+        return RCS_ERR_CUDA;
+      }
+      StepGraph g;
+      g.key = key;
+      g.launches = s->launches - launches0;
+      e = cudaGraphInstantiate(&g.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) {
+        s->err = std::string("CUDA error: ") + cudaGetErrorString(e) + " at cudaGraphInstantiate";
+        return RCS_ERR_CUDA;
+      }
+      CU_TRY(s, cudaGraphLaunch(g.exec, s->stream));  // the host-side half was done by step_enqueue itself
+      s->step_graphs.push_back(g);
+      s->graph_captures += 1;
+      return RCS_OK;
+    }
   }
-  return step_phase_b(s, dt, flags);
+  int rc = step_enqueue(s, dt, flags);
+  if (steady && rc == RCS_OK) {
+    s->recent_keys[1] = s->recent_keys[0];
+    s->recent_keys[0] = key;
+  }
+  return rc;
 }
 
 int rcs_sync(rcs_sim* s) {

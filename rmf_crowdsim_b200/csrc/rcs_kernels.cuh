@@ -89,6 +89,39 @@ struct PackArgs {
   AgentArrays cur;
 };
 
+// Strips: agent i of the owned agents sits in cell `idx`; if that is one of the outermost `width` columns of the
+// strip it is appended to the send buffer of that side (both, on a very narrow strip).
+__device__ __forceinline__ void halo_pack_one(const PackArgs& pk, uint32_t i, uint32_t idx, DevStatus* status) {
+  const uint32_t cx = idx / pk.nx;
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    const bool send = side == 0 ? (pk.has_left && cx < pk.st.c0 + pk.width) : (pk.has_right && cx + pk.width >= pk.st.c1);
+    if (!send) continue;
+    const HaloBuf& b = side == 0 ? pk.left : pk.right;
+    const uint32_t k = atomicAdd(b.count, 1u);
+    if (k >= b.cap) {
+      atomicAdd(&status->capacity_err, 1u);
+      continue;
+    }
+    b.pos[k] = pk.cur.pos[i];
+    b.vel[k] = pk.cur.vel[i];
+    b.id[k] = pk.cur.id[i];
+    b.meta[k] = (unsigned long long)pk.cur.grp[i] | ((unsigned long long)pk.cur.wp[i] << 32);
+    if (pk.cur.pv) b.pv[k] = pk.cur.pv[i];
+  }
+}
+
+// Strips, when the previous step's epilogue has already binned the owned agents (cellid, histogram): only the halo
+// pack of the binning pass is left to do.
+__global__ void halo_pack_kernel(uint32_t n_ub, const uint32_t* __restrict__ last, const uint32_t* __restrict__ cellid,
+                                 PackArgs pk, DevStatus* status) {
+  if (status->failed) return;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_ub || i >= *last) return;
+  const uint32_t c = cellid[i];
+  if (c != 0xffffffffu) halo_pack_one(pk, i, c, status);
+}
+
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 16;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
@@ -124,27 +157,13 @@ __global__ void bin_count_kernel(GridDev g, uint32_t n_ub, const uint32_t* __res
       return;
     }
     cellid[i] = (uint32_t)idx;
-    atomicAdd(&cell_count[idx], 1u);
-    if (pk.enabled) {
-      const uint32_t cx = (uint32_t)idx / pk.nx;
-#pragma unroll
-      for (int side = 0; side < 2; ++side) {
-        const bool send = side == 0 ? (pk.has_left && cx < pk.st.c0 + pk.width)
-                                    : (pk.has_right && cx + pk.width >= pk.st.c1);
-        if (!send) continue;
-        const HaloBuf& b = side == 0 ? pk.left : pk.right;
-        const uint32_t k = atomicAdd(b.count, 1u);
-        if (k >= b.cap) {
-          atomicAdd(&status->capacity_err, 1u);
-          continue;
-        }
-        b.pos[k] = p;
-        b.vel[k] = pk.cur.vel[i];
-        b.id[k] = pk.cur.id[i];
-        b.meta[k] = (unsigned long long)pk.cur.grp[i] | ((unsigned long long)pk.cur.wp[i] << 32);
-        if (pk.cur.pv) b.pv[k] = pk.cur.pv[i];
-      }
+    {
+      // The agents arrive in last step's canonical order, so the lanes of a warp fall into a handful of cells: one
+      // atomic per distinct cell of the warp instead of one per agent.
+      const unsigned peers = __match_any_sync(__activemask(), (uint32_t)idx);
+      if ((threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&cell_count[idx], (unsigned)__popc(peers));
     }
+    if (pk.enabled) halo_pack_one(pk, i, (uint32_t)idx, status);
   } else {
     // only reachable through snapshot injection; steps never commit an out-of-bounds position
     cellid[i] = CELL_DEAD;
@@ -286,7 +305,7 @@ __global__ void scatter_perm_kernel(uint32_t n_ub, const uint32_t* __restrict__ 
   if (i >= n_ub || i >= *n_ptr) return;
   uint32_t c = cellid[i];
   if (c == CELL_DEAD) return;
-  uint32_t pos = atomicAdd(&cursor[c], 1u);
+  uint32_t pos = atomicAdd(&cursor[c], 1u);  // (one atomic per distinct cell of the warp was measured: 1.5 x slower)
   perm[pos] = i;
 }
 
@@ -480,28 +499,53 @@ __device__ __forceinline__ uint4 query_slices(const GridDev& g, const uint32_t* 
   return sl;
 }
 
+// Staging ranges of one block of step_tile_kernel (rcs_step_tile.cuh): the union of its agents' slices per stencil
+// column.  Written here, by the block that gathers the same GATHER_THREADS agents.
+// Ranges start and end at even rows (the id rows are 8 bytes; bulk copies move multiples of 16 bytes from 16-byte
+// aligned addresses).  A block whose ranges hold more rows than its staging buffer does not stage.
+struct TileRange {
+  uint32_t lo[3];   // first sorted row of the range of stencil column d (even)
+  uint32_t len[3];  // rows (even); 0 = no agent of the block has such a slice
+};
+__device__ __forceinline__ bool st_takes(const GroupDev& g, uint64_t id, uint4 sl);
+__device__ __forceinline__ void st_block_ranges(bool takes, uint4 sl, uint32_t (*red)[6], TileRange* out);
+#ifndef RCS_TILE_WARPS
+#define RCS_TILE_WARPS 4
+#endif
+constexpr int ST_WARPS = RCS_TILE_WARPS;       // warps per block of step_tile_kernel
+constexpr int GATHER_THREADS = 32 * ST_WARPS;  // == block size of step_tile_kernel
+
 // One sorted slot per thread; positions and velocities move as 16-byte elements.  The arrays being gathered are
 // last step's sorted output and agents rarely change cell, so perm is close to the identity and the reads coalesce.
-__global__ void gather_sorted_kernel(uint32_t n, const uint32_t* __restrict__ perm, AgentArrays cur,
-                                     AgentArrays srt, const uint32_t* __restrict__ cellid,
-                                     uint32_t* __restrict__ srt_cell, const uint32_t* __restrict__ n_sorted,
-                                     GridDev g, const uint32_t* __restrict__ cell_start,
-                                     const GroupDev* __restrict__ groups, uint4* __restrict__ slices,
-                                     const DevStatus* status) {
-  if (status->failed) return;
+__global__ void __launch_bounds__(GATHER_THREADS) gather_sorted_kernel(
+    uint32_t n, const uint32_t* __restrict__ perm, AgentArrays cur, AgentArrays srt, const uint32_t* __restrict__ cellid,
+    uint32_t* __restrict__ srt_cell, const uint32_t* __restrict__ n_sorted, GridDev g,
+    const uint32_t* __restrict__ cell_start, const GroupDev* __restrict__ groups, uint4* __restrict__ slices,
+    TileRange* __restrict__ tile_ranges, const DevStatus* status) {
+  __shared__ uint32_t red[GATHER_THREADS / 32][6];
+  if (status->failed) return;  // block-uniform
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n || k >= *n_sorted) return;
-  const uint32_t i = perm[k];
-  const double2 p = cur.pos[i];
-  const uint32_t grp = cur.grp[i];
-  if (srt_cell) srt_cell[k] = cellid[i];
-  srt.pos[k] = p;
-  srt.vel[k] = cur.vel[i];
-  srt.id[k] = cur.id[i];
-  srt.grp[k] = grp;
-  srt.wp[k] = cur.wp[i];
-  if (cur.pv) srt.pv[k] = cur.pv[i];
-  if (slices) slices[k] = query_slices(g, cell_start, groups[grp], p.x, p.y);
+  bool takes = false;
+  uint4 sl = make_uint4(0u, 0u, 0u, 0u);
+  if (k < n && k < *n_sorted) {
+    const uint32_t i = perm[k];
+    const double2 p = cur.pos[i];
+    const uint32_t grp = cur.grp[i];
+    const uint64_t id = cur.id[i];
+    if (srt_cell) srt_cell[k] = cellid[i];
+    srt.pos[k] = p;
+    srt.vel[k] = cur.vel[i];
+    srt.id[k] = id;
+    srt.grp[k] = grp;
+    srt.wp[k] = cur.wp[i];
+    if (cur.pv) srt.pv[k] = cur.pv[i];
+    if (slices) {
+      sl = query_slices(g, cell_start, groups[grp], p.x, p.y);
+      slices[k] = sl;
+      takes = st_takes(groups[grp], id, sl);
+    }
+  }
+  if (tile_ranges) st_block_ranges(takes, sl, red, tile_ranges + blockIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -539,6 +583,12 @@ struct StepArgs {
   uint32_t* slow_list;             // warp kernel: agents left to the sequential routine
   uint32_t* wide_list;             // warp kernel: agents left to the chunked cooperative routine
   const uint4* slices;             // candidate slices prepared by gather_sorted_kernel (sorted path only)
+  const TileRange* tile_ranges;    // per block of step_tile_kernel: rows to stage (gather_sorted_kernel)
+  // Binning ahead: the epilogue files every agent that stays under the cell of the position the NEXT step starts
+  // from (A1 / A2 of that step: cell id + histogram), so that step's rebuild starts at the prefix sum.
+  uint32_t* next_cellid;           // nullptr: off
+  uint32_t* next_count;
+  uint64_t cell_lo, cell_hi;       // cells this handle indexes
   const double* routes;            // HL_ROUTE polylines, interleaved x,y
   double route_thr2;               // smallest double T with sqrt(T) >= 1e-1 (rmf/mod.rs:202)
 };
@@ -558,6 +608,13 @@ __device__ __forceinline__ uint32_t agent_role(const StepArgs& a, uint32_t i) {
   if (cx >= a.strip.c0 && cx < a.strip.c1) return ROLE_OWN;
   if (cx + a.strip.h >= a.strip.c0 && cx < a.strip.c1 + a.strip.h) return ROLE_RING;
   return ROLE_PASSIVE;
+}
+
+// An entry of the sorted arrays that this rank does not advance (ghost beyond the ring, slot beyond the live count):
+// it is not part of the next state.
+__device__ __forceinline__ void drop_entry(const StepArgs& a, uint32_t i) {
+  if (a.keep) a.keep[i] = 0u;
+  if (a.next_cellid) a.next_cellid[i] = CELL_DEAD;
 }
 
 struct Self {
@@ -784,6 +841,19 @@ __device__ __forceinline__ void integrate_and_store(const StepArgs& a, uint32_t 
   }
   if (a.no_commit) keep = own;  // the pre-step snapshot stays: this rank keeps exactly what it owned
   if (a.keep) a.keep[i] = keep ? 1u : 0u;
+  if (a.next_cellid) {
+    // location_to_index (A1) of the position the next step starts from: the new one, or -- without commit -- the old
+    uint64_t c = idx;
+    bool cin = inb;
+    if (a.no_commit) cin = location_to_index(a.grid, me.px, me.py, c);
+    if (keep && cin && c >= a.cell_lo && c < a.cell_hi) {
+      a.next_cellid[i] = (uint32_t)c;
+      atomicAdd(&a.next_count[c], 1u);
+    } else {
+      a.next_cellid[i] = CELL_DEAD;
+      if (keep && cin) atomicAdd(&a.status->halo_err, 1u);  // outside the cells this rank indexes (bin_count_kernel)
+    }
+  }
 }
 
 __device__ __forceinline__ void warp_stats(const StepArgs& a, uint32_t cand, uint32_t nbc, uint32_t finite) {
@@ -805,7 +875,7 @@ __device__ __forceinline__ void step_one_agent(const StepArgs& a, uint32_t i, ui
                                                uint32_t& finite) {
   const uint32_t role = agent_role(a, i);
   if (role == ROLE_PASSIVE) {
-    if (a.keep) a.keep[i] = 0u;
+    drop_entry(a, i);
     return;
   }
   const GroupDev& g = a.groups[a.in.grp[i]];
@@ -842,7 +912,7 @@ __global__ void __launch_bounds__(128) step_kernel(StepArgs a) {
   uint32_t n_live = *a.n_sorted;
   uint32_t cand = 0, nbc = 0, finite = 0;
   if (i < a.n && i < n_live) step_one_agent(a, i, cand, nbc, finite);
-  else if (a.keep && i < a.n) a.keep[i] = 0u;
+  else if (i < a.n) drop_entry(a, i);
   warp_stats(a, cand, nbc, finite);
 }
 

@@ -358,10 +358,10 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 6) step_warp_kernel(StepArgs a)
     role = agent_role(a, i);
     if (role == ROLE_PASSIVE) {
       active = false;
-      if (a.keep) a.keep[i] = 0u;
+      drop_entry(a, i);
     }
-  } else if (a.keep && i < a.n) {
-    a.keep[i] = 0u;
+  } else if (i < a.n) {
+    drop_entry(a, i);
   }
   if (active) {
     const GroupDev& g = a.groups[grp];

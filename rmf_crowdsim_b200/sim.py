@@ -580,6 +580,12 @@ class Simulation:
     def flush_l2(self, nbytes: int = 256 << 20) -> None:
         N.check(self._h, self._lib.rcs_flush_l2(self._h, nbytes))
 
+    def graph_stats(self) -> Tuple[int, int]:
+        """(steps that ran as one CUDA graph launch, graphs captured) -- RCS_OPT_GRAPHS."""
+        a, b = C.c_uint64(), C.c_uint64()
+        N.check(self._h, self._lib.rcs_graph_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def launch_count(self) -> int:
         out = C.c_uint64()
         N.check(self._h, self._lib.rcs_launch_count(self._h, C.byref(out)))

@@ -40,6 +40,61 @@ def build(lp_none: bool, device: int = 0, cols: int = 32, rows: int = 256):
     return sim, n_src, dom
 
 
+def measure(lp_none: bool, K: int, W: int, peaks: dict) -> dict:
+    """Short form for bench.py's `secondary` table: fill the building, W warm-up steps, K timed committed steps."""
+    from . import _native as N
+    from .sim import Duration
+    from bench import ALGO_BYTES_NOLOCALPLAN, ALGO_BYTES_ZANLUNGO
+
+    sim, n_src, dom = build(lp_none)
+    lib, h = sim._lib, sim._h
+    dt = Duration(0, 100_000_000)
+
+    def steps(k):
+        for _ in range(k):
+            N.check(h, lib.rcs_step_async(h, dt.secs, dt.nanos, N.RCS_STEP_DEFAULT))
+
+    done = 0
+    while done < 1400:  # one route takes ~1256 steps; events are drained so the buffers never overflow
+        steps(100)
+        sim.sync()
+        sim._dispatch_events()
+        done += 100
+    steps(W)
+    sim.sync()
+    sim._dispatch_events()
+    n_before = sim.agent_count()
+    steps(4)  # after the sync: new counts, new buffer roles -- the steps are captured as a graph again
+    launches0 = sim.launch_count()
+    sim.event_record(0)
+    steps(K)
+    sim.event_record(1)
+    sim.sync()
+    total_ms = sim.event_elapsed_ms(0, 1)
+    launches = sim.launch_count() - launches0
+    st = sim.stats()
+    n_after = sim.agent_count()
+    sim._dispatch_events()
+    N.check(h, lib.rcs_kernel_timing(h, 1))  # the dominant kernel, second short pass (kernel by kernel)
+    steps(min(K, 8))
+    sim.sync()
+    kt_ms, kt_n = C.c_double(), C.c_uint64()
+    N.check(h, lib.rcs_kernel_time_ms(h, C.byref(kt_ms), C.byref(kt_n)))
+    N.check(h, lib.rcs_kernel_timing(h, 0))
+    sim._dispatch_events()
+    n_mean = 0.5 * (n_before + n_after)
+    k_ms = kt_ms.value / max(kt_n.value, 1)
+    algo = ALGO_BYTES_NOLOCALPLAN if lp_none else ALGO_BYTES_ZANLUNGO
+    sim.spatial_index.close()
+    return {"workload": f"C5: SourceSink stream, {n_src} sources, device-side route follower, "
+                        f"{'NoLocalPlan' if lp_none else 'Zanlungo'}",
+            "agents": n_after, "mode": "committed steps (spawn + despawn every step)",
+            "value": n_mean * K / (total_ms * 1e-3), "ms_per_step": total_ms / K, "kernel_ms": k_ms,
+            "frac": algo * n_mean / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if k_ms > 0 else None,
+            "frac_whole_step": algo * n_mean * K / (total_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+            "nonfinite": int(st.nonfinite_count), "launches_per_step": launches / K, "steps": K}
+
+
 def run(args) -> None:
     from . import _native as N
     from .sim import Duration
