@@ -65,6 +65,7 @@ struct NcclApi {
   int (*CommDestroy)(void*) = nullptr;
   int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
@@ -170,6 +171,11 @@ struct rcs_sim {
   rcs::SourceSinkDev* d_sources = nullptr;
   double* d_ss_wp = nullptr;
   uint32_t* d_blocked = nullptr;
+  // strips: spawn set of the step as a bitmap over the source ids: this rank's, every rank's (single-process
+  // transport: staging for the other ranks' bitmaps), and the sum over the ranks
+  uint32_t *d_ss_bits_local = nullptr, *d_ss_bits_parts = nullptr, *d_ss_bits = nullptr;
+  uint32_t ss_words = 0;
+  cudaEvent_t ev_flags = nullptr;
   uint32_t *d_sg_start = nullptr, *d_sg_items = nullptr;
   rcs::SourceGridDev sgrid{};
   bool sources_dirty = false;

@@ -120,6 +120,7 @@ void rcs_sim_destroy(rcs_sim* s) {
   cudaFree(s->tr_nbids); cudaFree(s->tr_id); cudaFree(s->tr_own); cudaFree(s->stage); cudaFree(s->flush_buf);
   cudaFree(s->slow_list); cudaFree(s->wide_list); cudaFree(s->keep); cudaFree(s->slices); cudaFree(s->tile_ranges); cudaFree(s->cnt); cudaFree(s->d_next_id); cudaFree(s->srt_cell);
   cudaFree(s->d_sources); cudaFree(s->d_ss_wp); cudaFree(s->d_blocked); cudaFree(s->d_sg_start);
+  cudaFree(s->d_ss_bits_local); cudaFree(s->d_ss_bits_parts); cudaFree(s->d_ss_bits);
   cudaFree(s->d_sg_items); cudaFree(s->ev_spawn_id); cudaFree(s->ev_destroyed); cudaFree(s->ev_spawn_xy);
   dist_teardown(s);
   if (s->h_status) cudaFreeHost(s->h_status);

@@ -31,10 +31,12 @@ static bool nccl_load(std::string& err) {
   a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
   a.Send = reinterpret_cast<decltype(a.Send)>(dlsym(h, "ncclSend"));
   a.Recv = reinterpret_cast<decltype(a.Recv)>(dlsym(h, "ncclRecv"));
+  a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(h, "ncclAllReduce"));
   a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(dlsym(h, "ncclGroupStart"));
   a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(dlsym(h, "ncclGroupEnd"));
   a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
-  if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.Send || !a.Recv || !a.GroupStart || !a.GroupEnd) {
+  if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.Send || !a.Recv || !a.AllReduce || !a.GroupStart ||
+      !a.GroupEnd) {
     err = "libnccl.so.2 lacks a required entry point";
     return false;
   }
@@ -94,7 +96,7 @@ static int strip_setup(rcs_sim* s, int rank, int world, uint64_t halo_capacity) 
     return RCS_ERR_ARG;
   }
   if (s->n != 0 || s->ever_had_sources) {
-    s->err = "rcs_dist_init must come before agents are added; source sinks are not supported on strips";
+    s->err = "rcs_dist_init must come before agents and source sinks are added";
     return RCS_ERR_ARG;
   }
   const uint64_t ny = s->grid.nx ? s->grid.len / s->grid.nx : 0;
@@ -162,6 +164,22 @@ static int strip_halo_width(rcs_sim* s) {
   return RCS_OK;
 }
 
+// Strips with source sinks: the ranks' spawn bitmaps are disjoint, their sum is the global spawn set of the step.
+static int step_spawn_set_nccl(rcs_sim* s) {
+  if (s->world == 1) {
+    CU_TRY(s, cudaMemcpyAsync(s->d_ss_bits, s->d_ss_bits_local, s->ss_words * sizeof(uint32_t),
+                              cudaMemcpyDeviceToDevice, s->stream));
+    return RCS_OK;
+  }
+  if (!s->nccl_comm) {
+    s->err = "strip handle has no communicator";
+    return RCS_ERR_NCCL;
+  }
+  NCCL_TRY(s, g_nccl.AllReduce(s->d_ss_bits_local, s->d_ss_bits, s->ss_words, /*ncclUint32*/ 3, /*ncclSum*/ 0,
+                               s->nccl_comm, s->stream));
+  return RCS_OK;
+}
+
 static int step_exchange_nccl(rcs_sim* s) {
   if (s->world == 1) return RCS_OK;
   if (!s->nccl_comm) {
@@ -194,7 +212,8 @@ static void dist_teardown(rcs_sim* s) {
   halo_free(s->recv_r);
   if (s->ev_packed) cudaEventDestroy(s->ev_packed);
   if (s->ev_copied) cudaEventDestroy(s->ev_copied);
-  s->ev_packed = s->ev_copied = nullptr;
+  if (s->ev_flags) cudaEventDestroy(s->ev_flags);
+  s->ev_packed = s->ev_copied = s->ev_flags = nullptr;
   // unlink from a single-process group: the other handles must not touch this one any more
   for (rcs_sim* o : s->local_group)
     if (o && o != s)
@@ -245,6 +264,7 @@ int rcs_dist_init_local(rcs_sim** sims, int32_t world, uint64_t halo_capacity) {
     if (rc) return rc;
     CU_TRY(s, cudaEventCreateWithFlags(&s->ev_packed, cudaEventDisableTiming));
     CU_TRY(s, cudaEventCreateWithFlags(&s->ev_copied, cudaEventDisableTiming));
+    CU_TRY(s, cudaEventCreateWithFlags(&s->ev_flags, cudaEventDisableTiming));
     s->local_group.assign(sims, sims + world);
   }
   return RCS_OK;
@@ -257,10 +277,34 @@ int rcs_dist_step_local(rcs_sim** sims, int32_t world, uint64_t secs, uint32_t n
     rcs_sim* s = sims[r];
     if (!s || (int)s->local_group.size() != world || s->local_group[r] != s) return RCS_ERR_ARG;
   }
+  bool any_sources = false;
   for (int r = 0; r < world; ++r) {
     rcs_sim* s = sims[r];
     CU_TRY(s, cudaSetDevice(s->device));
-    int rc = step_phase_a(s, dt);
+    int rc = step_phase_a1(s, dt);
+    if (rc) return rc;
+    any_sources = any_sources || s->n_sources_alive != 0;
+    if (s->n_sources_alive) CU_TRY(s, cudaEventRecord(s->ev_flags, s->stream));
+  }
+  for (int r = 0; r < world; ++r) {
+    rcs_sim* s = sims[r];
+    CU_TRY(s, cudaSetDevice(s->device));
+    if (any_sources) {
+      // the spawn set of the step: every rank's bitmap, summed (what ncclAllReduce does between processes)
+      if (!s->n_sources_alive || s->ss_words != sims[0]->ss_words) {
+        s->err = "every rank of a strip group must hold the same source sinks";
+        return RCS_ERR_ARG;
+      }
+      for (int q = 0; q < world; ++q) {
+        if (q != r) CU_TRY(s, cudaStreamWaitEvent(s->stream, sims[q]->ev_flags, 0));
+        CU_TRY(s, cudaMemcpyAsync(s->d_ss_bits_parts + (size_t)q * s->ss_words, sims[q]->d_ss_bits_local,
+                                  s->ss_words * sizeof(uint32_t), cudaMemcpyDefault, s->stream));
+      }
+      ss_bits_sum_kernel<<<blocks_for(s->ss_words, 256), 256, 0, s->stream>>>(s->ss_words, (uint32_t)world,
+                                                                             s->d_ss_bits_parts, s->d_ss_bits);
+      s->launches += 1;
+    }
+    int rc = step_phase_a2(s, dt);
     if (rc) return rc;
   }
   for (int r = 0; r < world; ++r) {

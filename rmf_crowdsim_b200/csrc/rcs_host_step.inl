@@ -31,6 +31,14 @@ static int upload_sources(rcs_sim* s) {
   CU_TRY(s, cudaMemcpy(s->d_sources, s->sources.data(), ns * sizeof(SourceSinkDev), cudaMemcpyHostToDevice));
   CU_TRY(s, cudaMemcpy(s->d_ss_wp, s->ss_wp.data(), s->ss_wp.size() * sizeof(double), cudaMemcpyHostToDevice));
   CU_TRY(s, cudaMemset(s->d_blocked, 0, std::max<size_t>(ns, 1) * sizeof(uint32_t)));
+  if (s->strip.enabled) {
+    cudaFree(s->d_ss_bits_local); cudaFree(s->d_ss_bits_parts); cudaFree(s->d_ss_bits);
+    s->d_ss_bits_local = s->d_ss_bits_parts = s->d_ss_bits = nullptr;
+    s->ss_words = (uint32_t)((ns + 31) / 32);
+    CU_TRY(s, dalloc(&s->d_ss_bits_local, s->ss_words));
+    CU_TRY(s, dalloc(&s->d_ss_bits, s->ss_words));
+    CU_TRY(s, dalloc(&s->d_ss_bits_parts, (uint64_t)s->ss_words * std::max(s->world, 1)));
+  }
   // lookup grid over the alive sources (cells >= 1 m, at most 1024 x 1024 of them)
   double x0 = 0, y0 = 0, x1 = 0, y1 = 0;
   bool any = false;
@@ -158,7 +166,13 @@ static uint32_t spawn_launch_bound(rcs_sim* s) {
   return s->n_coarse;
 }
 
-static int step_phase_a(rcs_sim* s, double dt) {
+static int step_spawn_set_nccl(rcs_sim* s);  // rcs_host_dist.inl
+static void strip_range(const rcs_sim* s, int rank, int world, uint64_t& c0, uint64_t& c1);
+
+// Phase A, first half: counters reset; with source sinks the spawn probe (lib.rs:212-214) -- and on a strip this
+// rank's part of the step's spawn set, which is then summed over the ranks (step_spawn_set_nccl or the peer copies of
+// rcs_dist_step_local) before the second half.
+static int step_phase_a1(rcs_sim* s, double dt) {
   int rc = upload_groups(s);
   if (rc) return rc;
   rc = upload_routes(s);
@@ -176,15 +190,35 @@ static int step_phase_a(rcs_sim* s, double dt) {
                                             s->strip.enabled ? s->send_r.buf.count : nullptr);
   s->launches += 1;
   if (s->n_sources_alive) {
-    const uint32_t n_before = s->n_ub;
+    const uint32_t n_before = s->strip.enabled ? (uint32_t)s->cap : s->n_ub;
+    // On a strip the probe looks at the owned agents only: a source sink is accepted only where its whole probe
+    // stencil lies in its owner's columns (rcs_add_source_sink), and a rank owns exactly the agents in its columns.
     if (n_before)
       ss_probe_kernel<<<blocks_for(n_before, 256), 256, 0, s->stream>>>(
           s->grid, s->sgrid, s->d_sources, radius_threshold(0.4), n_before, s->cnt + CNT_CUR, s->cur.pos,
           s->cur_has_dead ? s->keep : nullptr, s->d_blocked, s->d_status);
+    s->launches += 1;
+    if (s->strip.enabled) {
+      CU_TRY(s, cudaMemsetAsync(s->d_ss_bits_local, 0, s->ss_words * sizeof(uint32_t), s->stream));
+      ss_flags_kernel<<<blocks_for(s->sources.size(), 256), 256, 0, s->stream>>>(
+          s->d_sources, (uint32_t)s->sources.size(), dt, s->d_blocked, s->d_ss_bits_local, s->d_status);
+      s->launches += 1;
+    }
+  }
+  CU_TRY(s, cudaGetLastError());
+  return RCS_OK;
+}
+
+// Phase A, second half: spawn at most one agent per source (lib.rs:199-254); strips: bin the owned agents and pack
+// the boundary columns for the neighbours.
+static int step_phase_a2(rcs_sim* s, double dt) {
+  int rc = RCS_OK;
+  if (s->n_sources_alive) {
     ss_spawn_kernel<<<1, SCAN_THREADS, 0, s->stream>>>(s->grid, s->d_sources, s->d_groups, (uint32_t)s->sources.size(), dt,
+                                                       s->strip.enabled ? s->d_ss_bits : nullptr,
                                                        s->d_blocked, s->cur, s->keep, (uint32_t)s->cap, s->cnt, s->d_next_id,
                                                        s->ev_spawn_id, s->ev_spawn_xy, s->ev_cap, s->d_status);
-    s->launches += 2;
+    s->launches += 1;
     s->n_ub = spawn_launch_bound(s);
   }
   if (s->strip.enabled) {
@@ -193,6 +227,9 @@ static int step_phase_a(rcs_sim* s, double dt) {
     if (rc) return rc;
     if (s->binned_ahead) {
       rc = bin_agents(s, s->n_ub, nullptr, 0, true, true);  // binned by the last step's epilogue: halo pack only
+      if (rc) return rc;
+      if (s->n_sources_alive)  // ... except this step's spawns, behind the pre-spawn count
+        rc = bin_agents(s, s->n_ub, s->cnt + CNT_SAVE, s->n_sources_alive, true);
     } else {
       rc = clear_histogram(s);
       if (rc) return rc;
@@ -203,6 +240,16 @@ static int step_phase_a(rcs_sim* s, double dt) {
   }
   CU_TRY(s, cudaGetLastError());
   return RCS_OK;
+}
+
+static int step_phase_a(rcs_sim* s, double dt) {
+  int rc = step_phase_a1(s, dt);
+  if (rc) return rc;
+  if (s->strip.enabled && s->n_sources_alive) {
+    rc = step_spawn_set_nccl(s);
+    if (rc) return rc;
+  }
+  return step_phase_a2(s, dt);
 }
 
 // ---- exchange: NCCL point-to-point with the two strip neighbours -------------------------------------
@@ -475,10 +522,6 @@ int rcs_add_source_sink(rcs_sim* s, const rcs_source_sink_desc* d, uint64_t* out
     s->err = "a source sink needs at least one waypoint (the reference indexes waypoints[0], lib.rs:244)";
     return RCS_ERR_ARG;
   }
-  if (s->strip.enabled) {
-    s->err = "source sinks are not supported on strip-partitioned handles";
-    return RCS_ERR_ARG;
-  }
   uint64_t idx;
   if (!host_location_to_index(s->grid, d->source_x, d->source_y, idx)) {
     // the reference fails at the first spawn (lib.rs:146-149 -> :252); reported when the source is added
@@ -510,6 +553,31 @@ int rcs_add_source_sink(rcs_sim* s, const rcs_source_sink_desc* d, uint64_t* out
   q.grp = find_or_add_group(s, d->hl, d->lp, d->agent_eyesight_range, (int32_t)id);
   q.loop_forever = d->loop_forever ? 1u : 0u;
   q.alive = 1u;
+  q.owned = 1u;
+  if (s->strip.enabled) {
+    // Every rank holds every source sink (same calls in the same order: the group tables and the source ids agree);
+    // the rank whose strip holds the source's cell column spawns for it.  Its spawn probe (lib.rs:212-214) looks at
+    // the agents that rank owns, so the probe's whole stencil of cell columns must lie inside that strip -- the same
+    // verdict on every rank.
+    const uint64_t cx = host_f64_as_usize((d->source_x - g.offx) / g.res);
+    int owner = -1;
+    uint64_t oc0 = 0, oc1 = 0;
+    for (int r = 0; r < s->world; ++r) {
+      strip_range(s, r, s->world, oc0, oc1);
+      if (cx >= oc0 && cx < oc1) {
+        owner = r;
+        break;
+      }
+    }
+    const bool left_ok = owner == 0 || q.pl >= (long long)oc0;
+    const bool right_ok = owner == s->world - 1 || q.pr < (long long)oc1;
+    if (owner < 0 || !left_ok || !right_ok) {
+      s->err = "on strips a source sink must lie far enough inside its strip for its 0.4 m spawn probe to stay in the "
+               "strip's cell columns";
+      return RCS_ERR_ARG;
+    }
+    q.owned = owner == s->rank ? 1u : 0u;
+  }
   s->ss_wp.insert(s->ss_wp.end(), d->waypoints_xy, d->waypoints_xy + 2 * d->n_waypoints);
   s->sources.push_back(q);
   s->sources_dirty = true;

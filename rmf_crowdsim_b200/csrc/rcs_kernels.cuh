@@ -46,7 +46,7 @@ struct SourceSinkDev {
   uint32_t grp;             // group of the agents it spawns
   uint32_t loop_forever;
   uint32_t alive;           // 0 after remove_source_sink
-  uint32_t pad_;
+  uint32_t owned;           // strips: this rank owns the source's cell column and spawns for it (1 on a single handle)
 };
 
 // spatial strips: this rank owns cell columns [c0, c1); h = halo ring width
@@ -1380,41 +1380,73 @@ __global__ void ss_probe_kernel(GridDev g, SourceGridDev sg, const SourceSinkDev
   }
 }
 
+// Strips: which of this rank's sources spawn in this step, as a bitmap over the source ids.  The ranks' bitmaps are
+// disjoint (a source is owned by one rank); their sum over the ranks is the global spawn set, from which every rank
+// derives the same sequential ids (lib.rs:128-129: ids follow the order of the source sinks).
+__global__ void ss_flags_kernel(const SourceSinkDev* __restrict__ ss, uint32_t n_ss, double dt,
+                                const uint32_t* __restrict__ blocked, uint32_t* __restrict__ bits,
+                                const DevStatus* status) {
+  if (status->failed) return;
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_ss) return;
+  const SourceSinkDev& s = ss[k];
+  const uint64_t want = f64_as_usize(round(dt * s.rate));  // MonotonicCrowd, source_sink.rs:97-100
+  if (s.alive && s.owned && want > 0 && !blocked[k]) atomicOr(&bits[k >> 5], 1u << (k & 31u));
+}
+
+// bits[w] = sum over the ranks' bitmaps (single-process transport; disjoint bits, so the sum is the union)
+__global__ void ss_bits_sum_kernel(uint32_t n_words, uint32_t world, const uint32_t* __restrict__ parts,
+                                   uint32_t* __restrict__ bits) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_words) return;
+  uint32_t v = 0;
+  for (uint32_t r = 0; r < world; ++r) v += parts[(size_t)r * n_words + w];
+  bits[w] = v;
+}
+
 // One block.  Sources in ascending id order; at most ONE agent per source per step and only when the
 // generator asks for >= 1 (the reference's loop over spawn_number is commented out, lib.rs:207-219).
-// Ids are allocated sequentially (lib.rs:128-129) in that order.
+// Ids are allocated sequentially (lib.rs:128-129) in that order.  gbits != nullptr (strips): the global spawn set
+// (ss_flags_kernel, summed over the ranks) decides and numbers the spawns; this rank materialises its own sources'.
 __global__ void ss_spawn_kernel(GridDev g, const SourceSinkDev* __restrict__ ss, const GroupDev* __restrict__ groups,
-                                uint32_t n_ss, double dt,
+                                uint32_t n_ss, double dt, const uint32_t* __restrict__ gbits,
                                 uint32_t* __restrict__ blocked, AgentArrays cur, uint32_t* __restrict__ keep,
                                 uint32_t cap, uint32_t* cnt, unsigned long long* next_id, unsigned long long* ev_id, double* ev_xy, uint32_t ev_cap,
                                 DevStatus* status) {
   if (status->failed) return;
-  __shared__ uint32_t base;
-  if (threadIdx.x == 0) base = 0;
+  __shared__ uint32_t base_all, base_own;
+  if (threadIdx.x == 0) base_all = base_own = 0;
   __syncthreads();
   const uint32_t n0 = cnt[CNT_CUR];
   const unsigned long long id0 = *next_id;
   const uint32_t ev0 = cnt[CNT_EV_SPAWN];
   for (uint32_t b = 0; b < n_ss; b += SCAN_THREADS) {
     const uint32_t k = b + threadIdx.x;
-    uint32_t spawn = 0;
+    uint32_t spawn = 0, mine = 0;
     if (k < n_ss) {
       const SourceSinkDev& s = ss[k];
-      const uint64_t want = f64_as_usize(round(dt * s.rate));  // MonotonicCrowd, source_sink.rs:97-100
-      spawn = (s.alive && want > 0 && !blocked[k]) ? 1u : 0u;
+      if (gbits) {
+        spawn = (gbits[k >> 5] >> (k & 31u)) & 1u;
+      } else {
+        const uint64_t want = f64_as_usize(round(dt * s.rate));  // MonotonicCrowd, source_sink.rs:97-100
+        spawn = (s.alive && want > 0 && !blocked[k]) ? 1u : 0u;
+      }
+      mine = (spawn && s.owned) ? 1u : 0u;
       blocked[k] = 0u;
     }
-    uint32_t total;
-    const uint32_t rank = block_exclusive_scan(spawn, total);
-    const uint32_t off = base;
+    uint32_t total_all, total_own;
+    const uint32_t rank_all = block_exclusive_scan(spawn, total_all);
+    const uint32_t rank_own = block_exclusive_scan(mine, total_own);
+    const uint32_t off_all = base_all, off_own = base_own;
     __syncthreads();
-    if (spawn) {
-      const uint32_t slot = n0 + off + rank;
+    if (mine) {
+      const uint32_t slot = n0 + off_own + rank_own;
       if (slot < cap) {
         const SourceSinkDev& s = ss[k];
+        const unsigned long long id = id0 + off_all + rank_all;
         cur.pos[slot] = make_double2(s.sx, s.sy);
         cur.vel[slot] = make_double2(0.0, 0.0);
-        cur.id[slot] = id0 + off + rank;
+        cur.id[slot] = id;
         cur.grp[slot] = s.grp;
         // set_target(agent, waypoints[0], ..) right after the spawn (lib.rs:242-249): a route follower starts at
         // the head of its route
@@ -1423,9 +1455,9 @@ __global__ void ss_spawn_kernel(GridDev g, const SourceSinkDev* __restrict__ ss,
         if (cur.pv)
           cur.pv[slot] = make_double2(__longlong_as_double(0x7ff8000000000000LL),
                                       __longlong_as_double(0x7ff8000000000000LL));
-        const uint32_t e = ev0 + off + rank;
+        const uint32_t e = ev0 + off_own + rank_own;
         if (e < ev_cap) {
-          ev_id[e] = id0 + off + rank;
+          ev_id[e] = id;
           ev_xy[2 * e] = s.sx;
           ev_xy[2 * e + 1] = s.sy;
         } else {
@@ -1435,17 +1467,20 @@ __global__ void ss_spawn_kernel(GridDev g, const SourceSinkDev* __restrict__ ss,
         atomicAdd(&status->capacity_err, 1u);
       }
     }
-    if (threadIdx.x == 0) base = off + total;
+    if (threadIdx.x == 0) {
+      base_all = off_all + total_all;
+      base_own = off_own + total_own;
+    }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    uint32_t total = base;
+    uint32_t total = base_own;
     if (n0 + total > cap) total = cap - n0;
     cnt[CNT_CUR] = n0 + total;
     cnt[CNT_TOT] = n0 + total;
     cnt[CNT_EV_SPAWN] = (ev0 + total > ev_cap) ? ev_cap : ev0 + total;
-    *next_id = id0 + base;
-    status->spawned = base;
+    *next_id = id0 + base_all;
+    status->spawned = base_own;
   }
 }
 

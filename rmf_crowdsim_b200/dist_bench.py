@@ -198,6 +198,92 @@ def run(args) -> None:
     dist.destroy_process_group()
 
 
+def _gather_states(st, dist, torch, rank: int, world: int):
+    """(id, x, y, vx, vy) of every rank on all ranks (padded), as raw 64-bit words."""
+    n1 = len(st["id"])
+    counts = torch.zeros(world, dtype=torch.int64, device="cuda")
+    counts[rank] = n1
+    dist.all_reduce(counts)
+    nmax = max(int(counts.max().item()), 1)
+    mine = torch.zeros((5, nmax), dtype=torch.int64, device="cuda")
+    for r, k in enumerate(("id", "x", "y", "vx", "vy")):
+        mine[r, :n1] = torch.from_numpy(st[k].view(np.int64).copy()).cuda()
+    parts = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    return parts, counts
+
+
+def verify_stream(dist, torch, rank: int, world: int, local: int, K: int = 120) -> dict:
+    """SourceSink spawn / despawn on strips over the NCCL transport (BASELINE config 5 in small): 4 x world source
+    sinks, two per strip quarter, whose agents walk through the strip boundaries to sinks in other strips; ids come
+    from the per-step spawn bitmap summed over the ranks (ncclAllReduce).  K committed steps, then every rank's agents
+    against the same steps on one handle, bit for bit."""
+    from . import sim as S
+    from .strips import StripSimulation
+
+    cell, ncols = 2.0, 64 * world
+    dom = cell * ncols
+    za = (0.05, 1.0, 0.0, 0.5, 1.0, 0.2)
+
+    def sources():
+        out = []
+        for q in range(world):
+            x0 = (q + 0.5) * dom / world  # the middle of strip q
+            for k, (dx, y) in enumerate([(0.45 * dom, 10.0), (-0.45 * dom, 20.0), (0.3 * dom, 30.0), (0.3 * dom, 30.15)]):
+                y += 32.0 * q  # streams of different sources stay out of each other's eyesight
+                x1 = min(max(x0 + dx, 4.0), dom - 4.0)
+                sp = 1.5 if k == 2 else 1.0  # the faster lane of the overtaking pair has the lower ids
+                v = (sp if x1 > x0 else -sp, 0.0)
+                wps = [((x0 + x1) / 2, y), (x1, y)]
+                hl = S.ConstantVelocityPlan(v)
+                out.append(S.SourceSink((x0, y), 0.6, S.MonotonicCrowd(2.0), hl, S.Zanlungo(*za), [wps[-1]], False,
+                                        2.0))
+        return out
+
+    cap = 4 * world * 300
+    sim = StripSimulation(S.LocationHash2D(dom, dom, cell, (0.0, 0.0), capacity=cap, device=local), rank, world,
+                          fresh_nccl_id(dist, torch, rank), halo_capacity=2048)
+    keep = sources()
+    for ss in keep:
+        sim.add_source_sink(ss)
+    dt = S.Duration(0, 500_000_000)
+    for k in range(K):
+        sim.step_async(dt)
+        if k % 40 == 39:
+            sim.sync()
+            sim._dispatch_events()
+    sim.sync()
+    st = sim.read_state()
+    parts, counts = _gather_states(st, dist, torch, rank, world)
+    ok, detail, n_ref = True, "", 0
+    if rank == 0:
+        got = np.concatenate([parts[r][:, : int(counts[r].item())].cpu().numpy() for r in range(world)], axis=1)
+        got = got[:, np.argsort(got[0].view(np.uint64), kind="stable")]
+        single = S.Simulation(S.LocationHash2D(dom, dom, cell, (0.0, 0.0), capacity=cap, device=local))
+        keep2 = sources()
+        for ss in keep2:
+            single.add_source_sink(ss)
+        for k in range(K):
+            single.step_async(dt)
+            if k % 40 == 39:
+                single.sync()
+                single._dispatch_events()
+        single.sync()
+        ref = single.read_state()
+        n_ref = len(ref["id"])
+        want = np.stack([ref[k].view(np.int64) for k in ("id", "x", "y", "vx", "vy")])
+        ok = got.shape == want.shape and bool(np.array_equal(got, want))
+        if not ok:
+            detail = f"shapes {got.shape} vs {want.shape}"
+        single.spatial_index.close()
+    sim.spatial_index.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    return {"ok": bool(int(flag.item())), "n_gpus": world, "steps": K, "source_sinks": 4 * world, "live_agents": n_ref,
+            "transport": "NCCL send/recv + all-reduce of the spawn bitmap", "workload": "SourceSink stream on strips",
+            "detail": detail}
+
+
 def verify_core(dist, torch, rank: int, world: int, local: int, workload: str, variant: str, dt, K: int) -> dict:
     """K COMMITTED steps of `workload` on `world` ranks over the NCCL transport; every rank's agents are gathered on
     rank 0 and compared bit for bit (ids, x, y, vx, vy) with the same steps on one handle.  Returns the verdict on
@@ -220,16 +306,7 @@ def verify_core(dist, torch, rank: int, world: int, local: int, workload: str, v
     stats = sim.stats()
     st = sim.read_state()
     n1 = len(st["id"])
-    # gather (id, x, y, vx, vy) of every rank on all ranks (padded), as raw 64-bit words
-    counts = torch.zeros(world, dtype=torch.int64, device="cuda")
-    counts[rank] = n1
-    dist.all_reduce(counts)
-    nmax = int(counts.max().item())
-    mine = torch.zeros((5, nmax), dtype=torch.int64, device="cuda")
-    for r, k in enumerate(("id", "x", "y", "vx", "vy")):
-        mine[r, :n1] = torch.from_numpy(st[k].view(np.int64).copy()).cuda()
-    parts = [torch.zeros_like(mine) for _ in range(world)]
-    dist.all_gather(parts, mine)
+    parts, counts = _gather_states(st, dist, torch, rank, world)
     mig = torch.tensor([abs(n1 - n0), stats.finite_tti_count], dtype=torch.int64, device="cuda")
     dist.all_reduce(mig)
     ok, detail = True, ""
@@ -290,6 +367,11 @@ def verify(args) -> None:
         if rank == 0:
             r["verify_dist"] = "ok" if r["ok"] else "FAILED"
             print(json.dumps(r), flush=True)
+    r = verify_stream(dist, torch, rank, world, local)
+    ok = ok and r["ok"]
+    if rank == 0:
+        r["verify_dist"] = "ok" if r["ok"] else "FAILED"
+        print(json.dumps(r), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if not ok:

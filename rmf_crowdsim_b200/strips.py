@@ -172,3 +172,18 @@ class LocalStripGroup:
 
     def agent_counts(self) -> List[int]:
         return [sm.agent_count() for sm in self.sims]
+
+    def add_source_sink(self, make_source_sink) -> int:
+        """Every rank holds every source sink (same calls in the same order); the rank that owns the source's cell
+        column spawns for it.  `make_source_sink()` returns a fresh SourceSink (planner objects are per handle)."""
+        ids = [sm.add_source_sink(make_source_sink()) for sm in self.sims]
+        assert len(set(ids)) == 1
+        return ids[0]
+
+    def add_event_listener(self, listener) -> None:
+        for sm in self.sims:
+            sm.add_event_listener(listener)
+
+    def dispatch_events(self) -> None:
+        for sm in self.sims:
+            sm._dispatch_events()

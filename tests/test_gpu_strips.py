@@ -187,3 +187,93 @@ def test_random_strip_configurations_match_one_handle(seed):
                 assert np.array_equal(tg[key].view(np.uint64), ts[key].view(np.uint64)), (key, k)
             _same(single.read_state(), grp.read_state())
     assert sum(grp.agent_counts()) == scene.n
+
+
+def _stream_scene():
+    """An empty 96 m x 96 m domain (48 cell columns of 2 m): the agents all come from source sinks."""
+    return SC.Scene(name="stream", width=96.0, height=96.0, cell=2.0, offset=(0.0, 0.0), xy=np.zeros((0, 2)),
+                    vxy=np.zeros((0, 2)), eyesight=2.0, hl=("constant", (0.0, 0.0)),
+                    lp=("zanlungo", 0.05, 1.0, 0.0, 0.5, 1.0, 0.2), seed=0)
+
+
+def _stream_sources(zan):
+    """Eight source sinks whose agents walk +x or -x across the strip boundaries (columns 16 and 32 for three
+    ranks), two of them as an overtaking pair 0.15 m apart (finite t_i with the Zanlungo planner); route followers
+    and constant-velocity planners; the sinks lie in other strips than the sources."""
+    za = (0.05, 1.0, 0.0, 0.5, 1.0, 0.2)
+    specs = []
+    for k, (x0, x1, y) in enumerate([(5.0, 85.0, 10.0), (85.0, 9.0, 20.0), (41.0, 90.0, 30.0), (53.0, 7.0, 40.0),
+                                     (11.0, 70.0, 50.0), (11.0, 70.0, 50.15), (75.0, 40.0, 60.0), (21.0, 50.0, 70.0)]):
+        sp = 1.5 if k == 4 else 1.0  # the faster lane has the lower ids (it yields): stays finite, as in _pair()
+        v = (sp if x1 > x0 else -sp, 0.0)
+        # route followers in single file go NaN under the Zanlungo planner (SURVEY.md 0.4): constant planners there
+        route = k % 2 == 0 and k != 4 and not zan
+        specs.append(((x0, y), [((x0 + x1) / 2, y + (0.5 if route else 0.0)), (x1, y)], v, route))
+
+    def maker(spec):
+        src, wps, v, route = spec
+
+        def make():
+            hl = R.RouteFollowPlan(wps) if route else R.ConstantVelocityPlan(v)
+            lp = R.Zanlungo(*za) if zan else R.NoLocalPlan()
+            return R.SourceSink(src, 0.6, R.MonotonicCrowd(2.0), hl, lp, [wps[-1]], False, 2.0)
+        return make
+    return [maker(sp) for sp in specs]
+
+
+class _Rec(R.EventListener):
+    def __init__(self):
+        self.added, self.removed = [], []
+
+    def agent_spawned(self, position, agent):
+        self.added.append((agent, position))
+
+    def agent_destroyed(self, agent):
+        self.removed.append(agent)
+
+
+@pytest.mark.parametrize("zan", [False, True])
+def test_source_sinks_on_strips_match_one_handle(zan):
+    """SourceSink spawn / despawn on a strip-partitioned crowd (lib.rs:199-254, 305-336): each rank spawns for the
+    sources in its columns, the ids come from the step's global spawn set (a bitmap summed over the ranks), agents
+    migrate through the strips to sinks owned by other ranks.  Ids, states and events equal one handle's."""
+    scene = _stream_scene()
+    single = SC.build_simulation(scene, capacity=4096)
+    grp = LocalStripGroup(scene, 3, capacity=4096, halo_capacity=1024)
+    rec_s, rec_g = _Rec(), _Rec()
+    single.add_event_listener(rec_s)
+    grp.add_event_listener(rec_g)
+    keep = []
+    for make in _stream_sources(zan):
+        ss = make()
+        keep.append(ss)
+        single.add_source_sink(ss)
+        grp.add_source_sink(make)
+    dt = R.Duration(0, 500_000_000)
+    for step in range(130):
+        single.step(dt)
+        grp.step(dt)
+        grp.dispatch_events()
+        if step % 10 == 9 or step > 120:
+            sa, sb = single.read_state(), grp.read_state()
+            assert np.array_equal(sa["id"], sb["id"]), step
+            for k in ("x", "y", "vx", "vy"):
+                assert np.array_equal(sa[k].view(np.uint64), sb[k].view(np.uint64)), (k, step)
+            assert np.array_equal(sa["next_waypoint"], sb["next_waypoint"])
+    assert sorted(rec_g.added) == sorted(rec_s.added) and len(rec_s.added) > 500
+    assert sorted(rec_g.removed) == sorted(rec_s.removed) and len(rec_s.removed) > 100
+    counts = grp.agent_counts()
+    assert sum(counts) == single.agent_count() and min(counts) > 0
+
+
+def test_source_sink_next_to_a_strip_boundary_is_refused():
+    scene = _stream_scene()
+    grp = LocalStripGroup(scene, 3, capacity=256, halo_capacity=128)
+
+    def make(x):
+        return lambda: R.SourceSink((x, 10.0), 0.6, R.MonotonicCrowd(2.0), R.ConstantVelocityPlan((1.0, 0.0)),
+                                    R.NoLocalPlan(), [(x + 5.0, 10.0)], False, 2.0)
+    with pytest.raises(R.CrowdsimError):
+        grp.add_source_sink(make(32.2))  # column 16 is rank 1's first: the 0.4 m probe reaches into column 15
+    grp.add_source_sink(make(33.0))      # probe columns 16..16
+    grp.add_source_sink(make(0.1))       # the domain's edge is nobody's boundary
