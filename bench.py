@@ -564,12 +564,12 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
-    if args.workload == "c5":
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload == "c5" and args.gpus == 1 and world == 1:
         from rmf_crowdsim_b200 import stream_bench
 
         stream_bench.run(args)
         return
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus == 1 and world == 1:
         run_gpu_single(args)
     elif world == 1:
@@ -583,6 +583,8 @@ def main():
 
         if args.verify_dist:
             dist_bench.verify(args)
+        elif args.workload == "c5":
+            dist_bench.run_stream(args)
         else:
             dist_bench.run(args)
 

@@ -289,6 +289,73 @@ impl Simulation {
     }
 }
 
+/// spatial_index/spatial_index.rs:4-14, verbatim: the trait the reference's `Simulation<T: SpatialIndex>` is generic
+/// over.  `GpuLocationHash2D` implements it, so code written against the trait (or against `LocationHash2D`'s own
+/// methods, location_hash_2d.rs:126-267) compiles unchanged with the device-backed index.  The trait's read methods
+/// take `&self`; the handle needs `&mut`, hence the `RefCell`, as single-threaded as the reference itself.
+pub trait SpatialIndex {
+    fn add_or_update(&mut self, id: AgentId, position: Point) -> Result<(), String>;
+    fn get_nearest_neighbours(&self, n: usize, position: Point) -> Vec<AgentId>;
+    fn get_neighbours_in_radius(&self, radius: f64, position: Point) -> Vec<AgentId>;
+    fn remove_agent(&mut self, _id: AgentId) {}
+}
+
+/// `LocationHash2D::new(width, height, cell_size, offset)` (location_hash_2d.rs:33-51) on the device, usable on its
+/// own (rcs_index_add_or_update / rcs_index_remove / rcs_query_radius / rcs_query_knn).
+pub struct GpuLocationHash2D {
+    sim: std::cell::RefCell<Simulation>,
+}
+
+impl GpuLocationHash2D {
+    pub fn new(width: f64, height: f64, cell_size: f64, offset: Point, capacity: usize, device: i32) -> Result<Self, String> {
+        Ok(GpuLocationHash2D { sim: std::cell::RefCell::new(Simulation::new(width, height, cell_size, offset, capacity, device)?) })
+    }
+}
+
+impl SpatialIndex for GpuLocationHash2D {
+    /// location_hash_2d.rs:126-149; `Err("Index out of bounds")` as the reference
+    fn add_or_update(&mut self, id: AgentId, position: Point) -> Result<(), String> {
+        let sim = self.sim.get_mut();
+        let (ids, xy) = ([id as u64], [position.x, position.y]);
+        check(sim.h, unsafe { sys::rcs_index_add_or_update(sim.h, 1, ids.as_ptr(), xy.as_ptr()) })
+    }
+    /// location_hash_2d.rs:151-238 (ring walk, quirks included)
+    fn get_nearest_neighbours(&self, n: usize, position: Point) -> Vec<AgentId> {
+        self.sim.borrow_mut().get_nearest_neighbours(n, position).unwrap_or_default()
+    }
+    /// location_hash_2d.rs:240-258 (strict `<`; cells x-major then y, ascending id inside a cell)
+    fn get_neighbours_in_radius(&self, radius: f64, position: Point) -> Vec<AgentId> {
+        self.sim.borrow_mut().get_neighbours_in_radius(radius, position).unwrap_or_default()
+    }
+    /// location_hash_2d.rs:260-267
+    fn remove_agent(&mut self, id: AgentId) {
+        let sim = self.sim.get_mut();
+        let ids = [id as u64];
+        let _ = unsafe { sys::rcs_index_remove(sim.h, 1, ids.as_ptr()) };
+    }
+}
+
+/// local_planners/local_planner.rs:7-18, verbatim.  The per-agent call cannot carry a device backend (one virtual call
+/// per agent per step, `Agent::preferred_vel` private: SURVEY.md 8b), so the descriptors implement it only as the
+/// planner's host-side definition for ONE agent -- what `Simulation::step` evaluates for all agents on the device.
+pub trait LocalPlanner {
+    fn get_desired_velocity(&self, agent: &Agent, nearby_agents: &Vec<Agent>, recommended_velocity: Vec2f) -> Vec2f;
+    fn add_agent(&mut self, _agent: AgentId) {}
+    fn remove_agent(&mut self, _agent: AgentId) {}
+}
+
+impl LocalPlanner for LocalPlan {
+    fn get_desired_velocity(&self, _agent: &Agent, _nearby_agents: &Vec<Agent>, recommended_velocity: Vec2f) -> Vec2f {
+        match self {
+            // no_local_plan.rs:10-17
+            LocalPlan::NoLocalPlan => recommended_velocity,
+            // zanlungo.rs:201-218 runs on the device inside Simulation::step; a one-agent host evaluation would need
+            // the private preferred_vel the reference hides from planners outside its crate
+            LocalPlan::Zanlungo { .. } => unimplemented!("Zanlungo is evaluated for the whole crowd by Simulation::step"),
+        }
+    }
+}
+
 impl Drop for Simulation {
     fn drop(&mut self) {
         unsafe { sys::rcs_sim_destroy(self.h) }

@@ -101,6 +101,7 @@ int rcs_sim_create(const rcs_sim_desc* desc, rcs_sim** out) {
   for (uint32_t k = 0; k < RCS_NUM_EVENTS; ++k) CR_TRY(cudaEventCreate(&s->events[k]));
 #undef CR_TRY
   s->stats.first_oob_id = ~0ull;
+  if (const char* e = std::getenv("RCS_GRAPHS")) s->opt_graphs = std::atoi(e) != 0 ? 1u : 0u;  // default of RCS_OPT_GRAPHS
   *out = s;
   return RCS_OK;
 }

@@ -347,6 +347,73 @@ def verify_core(dist, torch, rank: int, world: int, local: int, workload: str, v
 DIST_VERIFY = ("sparse256", "shuffled", (0, 33_333_333), 30)
 
 
+def run_stream(args) -> None:
+    """bench.py --gpus N --workload c5: the SourceSink stream of BASELINE config 5 on N strips (stream_bench.build):
+    8192 source sinks, ~2.3 M live agents, spawns and despawns every step, agents migrating between the ranks."""
+    import torch
+    import torch.distributed as dist
+
+    from . import _native as N
+    from . import sim as S
+    from . import stream_bench
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lp_none = not args.c5_zanlungo
+    check = None if getattr(args, "skip_verify", False) else verify_stream(dist, torch, rank, world, local)
+    sim, n_src, dom = stream_bench.build(lp_none, device=local, strip=(rank, world, fresh_nccl_id(dist, torch, rank)))
+    lib, h = sim._lib, sim._h
+    dt = S.Duration(0, 100_000_000)
+
+    def steps(k):
+        for _ in range(k):
+            N.check(h, lib.rcs_step_async(h, dt.secs, dt.nanos, N.RCS_STEP_DEFAULT))
+
+    done = 0
+    while done < 1400:  # fill the building; events are drained so the buffers never overflow
+        steps(100)
+        sim.sync()
+        sim._dispatch_events()
+        done += 100
+    n_before = sim.agent_count()
+    steps(8)  # after the sync: the launch sequence repeats again and is captured as a graph
+    launches0 = sim.launch_count()
+    K = args.steps
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sim.event_record(0)
+    steps(K)
+    sim.event_record(1)
+    sim.sync()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([sim.event_elapsed_ms(0, 1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    n_after = sim.agent_count()
+    st = sim.stats()
+    agg = torch.tensor([0.5 * (n_before + n_after), n_after, sim.launch_count() - launches0, st.nonfinite_count],
+                       dtype=torch.float64, device="cuda")
+    dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    sim._dispatch_events()
+    if rank == 0:
+        total_ms = float(ms.item())
+        print(json.dumps({
+            "metric": "agent-steps/sec (query+Zanlungo+integrate)", "value": agg[0].item() * K / (total_ms * 1e-3),
+            "unit": "agent-steps/s", "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": total_ms / K,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C5: SourceSink stream, {n_src} sources, device-side route follower, "
+                                   f"{'NoLocalPlan' if lp_none else 'Zanlungo'}, committed steps, {world} strips",
+                       "agents_live": int(agg[1].item()), "domain_m": dom, "nonfinite": int(agg[3].item())},
+            "e2e": None, "gpu_launches": int(agg[2].item()), "dist_verified": None if check is None else check["ok"],
+            "dist_verify": check, "roofline": None, "cpu_baseline": None}), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def verify(args) -> None:
     """bench.py --gpus N --verify-dist: the NCCL transport against one handle, bit for bit: first the lane-ordered
     crowd (long strides, many migrations, force pass idle), then the force-active sparse crowd."""

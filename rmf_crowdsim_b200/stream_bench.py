@@ -17,7 +17,10 @@ import time
 import numpy as np
 
 
-def build(lp_none: bool, device: int = 0, cols: int = 32, rows: int = 256):
+def build(lp_none: bool, device: int = 0, cols: int = 32, rows: int = 256, strip=None):
+    """strip = (rank, world, nccl_id): this rank of a strip-partitioned stream.  Every rank holds all source sinks;
+    the rank that owns a source's cell column spawns for it (source columns are 65 c + 17 of 2112: never next to a
+    boundary of 2, 4 or 8 equal strips)."""
     from . import sim as S
 
     margin, cell = 32.0, 2.0
@@ -25,8 +28,17 @@ def build(lp_none: bool, device: int = 0, cols: int = 32, rows: int = 256):
     dom = float(np.ceil((cols * pitch_x + 2 * margin) / cell) * cell)
     n_src = cols * rows
     cap = int(n_src * 330 * 1.1)  # ~314 agents per source in steady state
-    idx = S.LocationHash2D(dom, dom, cell, (-margin, -margin), capacity=cap, device=device)
-    sim = S.Simulation(idx)
+    if strip is None:
+        idx = S.LocationHash2D(dom, dom, cell, (-margin, -margin), capacity=cap, device=device)
+        sim = S.Simulation(idx)
+    else:
+        from .strips import StripSimulation
+
+        rank, world, nccl_id = strip
+        halo_cap = int(3 * rows * 2.5 * 1.5) + 4096  # three columns per side, ~2 agents per lane and column
+        cap = int(cap / world * 1.3) + 2 * halo_cap + 8192
+        idx = S.LocationHash2D(dom, dom, cell, (-margin, -margin), capacity=cap, device=device)
+        sim = StripSimulation(idx, rank, world, nccl_id, halo_capacity=halo_cap)
     lp = S.NoLocalPlan() if lp_none else S.Zanlungo(0.05, 1.0, 0.0, 0.5, 1.0, 0.2)
     keep = [lp]
     for c in range(cols):
