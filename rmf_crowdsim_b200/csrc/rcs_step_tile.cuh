@@ -149,10 +149,9 @@ __device__ __noinline__ void st_w0_literal(TileWarp& w, const GroupDev* groups, 
 // Stage 2, the queued pairs of a warp: the literal time_to_collision (sqrt, two divisions, root selection), one pair
 // per lane; the owner's terms come by shuffle, the minimum goes to the owner's slot by a shared atomicMin on the bit
 // pattern (collision times are >= +0, so integer order == float order, and min is order-independent).  Entered by
-// the whole warp after a __syncwarp(); leaves w.hcnt = 0.
-__device__ __noinline__ void st_flush_hits(TileWarp& w, const double2* spos, const double2* svel, unsigned lane,
-                                           double px, double py, double vx, double vy, double rr) {
-  const uint32_t n_hit = *(volatile uint32_t*)&w.hcnt;
+// the whole warp after a __syncwarp(); n_hit = entries in the list.
+__device__ __noinline__ void st_flush_hits(TileWarp& w, uint32_t n_hit, const double2* spos, const double2* svel,
+                                           unsigned lane, double px, double py, double vx, double vy, double rr) {
   for (uint32_t b = 0; b < n_hit; b += 32) {
     const uint32_t e = b + lane;
     const bool v = e < n_hit;
@@ -169,8 +168,6 @@ __device__ __noinline__ void st_flush_hits(TileWarp& w, const double2* spos, con
       if (ct < RCS_INF) atomicMin(&w.tbits[o], (unsigned long long)__double_as_longlong(ct));
     }
   }
-  __syncwarp();
-  if (lane == 0) w.hcnt = 0u;
   __syncwarp();
 }
 
@@ -368,9 +365,7 @@ __global__ void __launch_bounds__(32 * ST_WARPS, RCS_TILE_BLOCKS) step_tile_kern
   if (maxc) {
     // ---- stage 2: t_i = min over the list of time_to_collision (zanlungo.rs:76-91); y = entries with the higher id
     w.tbits[lane] = 0x7ff0000000000000ull;
-    if (lane == 0) w.hcnt = 0u;
     __syncwarp();
-    auto flush_hits = [&]() { st_flush_hits(w, spos, svel, lane, me.px, me.py, me.vx, me.vy, rr); };
     // the division-free half of time_to_collision for staged row j; same operations as rcs_math.cuh
     auto probe = [&](bool v, uint32_t j, uint32_t k, uint32_t& y) -> bool {
       const double2 c = spos[j], cv = svel[j];
@@ -391,27 +386,36 @@ __global__ void __launch_bounds__(32 * ST_WARPS, RCS_TILE_BLOCKS) step_tile_kern
       // compare also covers b*b = inf.  Everything else is decided by the literal routine on the list.
       return v && (qa > 0.0) && (disc >= 0.0) && ((qb < 0.0) || !(disc < bb));
     };
+    // Pairs that may return a finite time are queued per warp; slots come from ballots (no atomics, and the count is a
+    // register the whole warp agrees on, so nothing is read back from shared memory inside the loop).
+    uint32_t n_hit = 0;
+    const uint32_t lt = (1u << lane) - 1u;
     for (uint32_t k = 0; k < maxc; k += 2) {
       const bool vA = k < cnt, vB = k + 1u < cnt;
       const uint32_t jA = vA ? col[32u * k] : 0u;
       const uint32_t jB = vB ? col[32u * k + 32u] : 0u;
       const bool hitA = probe(vA, jA, k, y);
       const bool hitB = probe(vB, jB, k + 1u, y);
-      if (hitA) {  // order inside the list is irrelevant (min): a shared counter hands out the slots
-        const uint32_t p = atomicAdd(&w.hcnt, 1u);
+      const unsigned bA = __ballot_sync(FULL, hitA), bB = __ballot_sync(FULL, hitB);
+      if (hitA) {  // order inside the list is irrelevant (min)
+        const uint32_t p = n_hit + __popc(bA & lt);
         w.lj[p] = (uint16_t)jA;
         w.lo[p] = (uint8_t)lane;
       }
       if (hitB) {
-        const uint32_t p = atomicAdd(&w.hcnt, 1u);
+        const uint32_t p = n_hit + __popc(bA) + __popc(bB & lt);
         w.lj[p] = (uint16_t)jB;
         w.lo[p] = (uint8_t)lane;
       }
-      __syncwarp();
-      if (*(volatile uint32_t*)&w.hcnt > ST_CAP - 64u) flush_hits();  // at most 64 new entries per round
+      n_hit += __popc(bA) + __popc(bB);
+      if (n_hit > 2u * ST_CAP - 64u) {  // at most 64 new entries per round
+        __syncwarp();
+        st_flush_hits(w, n_hit, spos, svel, lane, me.px, me.py, me.vx, me.vy, rr);
+        n_hit = 0u;
+      }
     }
     __syncwarp();
-    if (*(volatile uint32_t*)&w.hcnt) flush_hits();
+    if (n_hit) st_flush_hits(w, n_hit, spos, svel, lane, me.px, me.py, me.vx, me.vy, rr);
     __syncwarp();
     if (fast) t_i = __longlong_as_double((long long)w.tbits[lane]);
   }
