@@ -367,9 +367,8 @@ __global__ void __launch_bounds__(32 * ST_WARPS, RCS_TILE_BLOCKS) step_tile_kern
     w.tbits[lane] = 0x7ff0000000000000ull;
     __syncwarp();
     // the division-free half of time_to_collision for staged row j; same operations as rcs_math.cuh
-    auto probe = [&](bool v, uint32_t j, uint32_t k, uint32_t& y) -> bool {
-      const double2 c = spos[j], cv = svel[j];
-      y |= (v && me.id < sid[j]) ? (1u << k) : 0u;
+    auto probe = [&](bool v, double2 c, double2 cv, unsigned long long oid, uint32_t k, uint32_t& y) -> bool {
+      y |= (v && me.id < oid) ? (1u << k) : 0u;
       const double dx = c.x - me.px;
       const double dy = c.y - me.py;
       const double rvx = cv.x - me.vx;
@@ -390,12 +389,15 @@ __global__ void __launch_bounds__(32 * ST_WARPS, RCS_TILE_BLOCKS) step_tile_kern
     // register the whole warp agrees on, so nothing is read back from shared memory inside the loop).
     uint32_t n_hit = 0;
     const uint32_t lt = (1u << lane) - 1u;
+    // list entries are fetched one iteration ahead (their shared-memory latency is off the dependent chain)
+    uint32_t jA_n = cnt > 0u ? col[0] : 0u, jB_n = cnt > 1u ? col[32u] : 0u;
     for (uint32_t k = 0; k < maxc; k += 2) {
       const bool vA = k < cnt, vB = k + 1u < cnt;
-      const uint32_t jA = vA ? col[32u * k] : 0u;
-      const uint32_t jB = vB ? col[32u * k + 32u] : 0u;
-      const bool hitA = probe(vA, jA, k, y);
-      const bool hitB = probe(vB, jB, k + 1u, y);
+      const uint32_t jA = jA_n, jB = jB_n;
+      jA_n = k + 2u < cnt ? col[32u * k + 64u] : 0u;
+      jB_n = k + 3u < cnt ? col[32u * k + 96u] : 0u;
+      const bool hitA = probe(vA, spos[jA], svel[jA], sid[jA], k, y);
+      const bool hitB = probe(vB, spos[jB], svel[jB], sid[jB], k + 1u, y);
       const unsigned bA = __ballot_sync(FULL, hitA), bB = __ballot_sync(FULL, hitB);
       if (hitA) {  // order inside the list is irrelevant (min)
         const uint32_t p = n_hit + __popc(bA & lt);
