@@ -460,14 +460,26 @@ __global__ void __launch_bounds__(32 * ST_WARPS, RCS_TILE_BLOCKS) step_tile_kern
         const bool part = lane >= lane_begin && lane < lane_end;
         if (part) {  // one walk over the list entries feeds both pair lists
           uint32_t pA = offA, pB = ST_CAP + offB;
-          for (uint32_t bits = ya | za; bits; bits &= bits - 1u) {
-            const uint32_t k = (uint32_t)(__ffs(bits) - 1);
-            const bool yv = ((ya >> k) & 1u) != 0u;
-            const uint32_t p = yv ? pA : pB;
-            w.lj[p] = col[32u * k];
-            w.lo[p] = (uint8_t)lane;
-            pA += yv ? 1u : 0u;
-            pB += yv ? 0u : 1u;
+          for (uint32_t bits = ya | za; bits;) {  // two entries per turn: their list reads are independent
+            const uint32_t k0 = (uint32_t)(__ffs(bits) - 1);
+            bits &= bits - 1u;
+            const bool two = bits != 0u;
+            const uint32_t k1 = two ? (uint32_t)(__ffs(bits) - 1) : k0;
+            bits &= bits - 1u;  // 0 stays 0
+            const uint16_t e0 = col[32u * k0], e1 = col[32u * k1];
+            const bool y0 = ((ya >> k0) & 1u) != 0u, y1 = ((ya >> k1) & 1u) != 0u;
+            const uint32_t p0 = y0 ? pA : pB;
+            w.lj[p0] = e0;
+            w.lo[p0] = (uint8_t)lane;
+            pA += y0 ? 1u : 0u;
+            pB += y0 ? 0u : 1u;
+            if (two) {
+              const uint32_t p1 = y1 ? pA : pB;
+              w.lj[p1] = e1;
+              w.lo[p1] = (uint8_t)lane;
+              pA += y1 ? 1u : 0u;
+              pB += y1 ? 0u : 1u;
+            }
           }
         }
         const uint32_t tot = __shfl_sync(FULL, inc, lane_end - 1) - base;
@@ -516,7 +528,15 @@ __global__ void __launch_bounds__(32 * ST_WARPS, RCS_TILE_BLOCKS) step_tile_kern
         }
         __syncwarp();
         if (part) {
-          for (uint32_t r = 0; r < cA; ++r) {
+          uint32_t r = 0;
+          for (; r + 1u < cA; r += 2u) {  // same order of additions, two loads in flight
+            const double2 q0 = w.sf[offA + r], q1 = w.sf[offA + r + 1u];
+            fx = fx + q0.x;
+            fy = fy + q0.y;
+            fx = fx + q1.x;
+            fy = fy + q1.y;
+          }
+          if (r < cA) {
             const double2 q = w.sf[offA + r];
             fx = fx + q.x;
             fy = fy + q.y;
