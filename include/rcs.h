@@ -274,6 +274,10 @@ int rcs_fp64_peak(int32_t device, double* out_tflops, double* out_dadd_tops);
  * through a flag in the halo header, its neighbours within the next steps; the job is then over. */
 int rcs_nccl_unique_id(uint8_t out_id[128]);
 int rcs_dist_init(rcs_sim* sim, int32_t rank, int32_t world, const uint8_t nccl_id[128], uint64_t halo_capacity);
+/* Optional, before rcs_dist_init, the same call on every rank: the strips' cell-column boundaries (world + 1 values
+ * rising strictly from 0 to the number of cell columns) instead of the equal split -- e.g. balanced by agent count
+ * when the crowd does not fill the grid.  bounds == NULL: back to the equal split. */
+int rcs_dist_set_boundaries(rcs_sim* sim, int32_t world, const uint64_t* bounds);
 /* Column range [c0, c1) owned by `rank` of `world` for this handle's grid. */
 int rcs_dist_strip(rcs_sim* sim, int32_t rank, int32_t world, uint64_t* c0, uint64_t* c1);
 /* add_agents with caller-supplied global ids (the global sequential allocation of lib.rs:128-129

@@ -190,6 +190,7 @@ struct rcs_sim {
   rcs::StripDev strip{};
   int rank = 0, world = 1;
   uint32_t halo_width = 0;  // columns sent to each neighbour = ring h + stencil reach q
+  std::vector<uint64_t> strip_bounds;  // optional: world + 1 column boundaries (rcs_dist_set_boundaries); empty = equal split
   rcs_host::HaloMem send_l, send_r, recv_l, recv_r;
   void* nccl_comm = nullptr;
   std::vector<rcs_sim*> local_group;  // single-process transport: the handles of all ranks, by rank

@@ -81,6 +81,11 @@ static void halo_free(HaloMem& m) {
 static uint64_t strip_columns(const rcs_sim* s) { return s->grid.x_max < 0 ? 0 : (uint64_t)s->grid.x_max + 1; }
 
 static void strip_range(const rcs_sim* s, int rank, int world, uint64_t& c0, uint64_t& c1) {
+  if ((int)s->strip_bounds.size() == world + 1) {  // caller-supplied boundaries (balanced by agent count)
+    c0 = s->strip_bounds[rank];
+    c1 = s->strip_bounds[rank + 1];
+    return;
+  }
   const uint64_t cols = strip_columns(s);
   c0 = cols * (uint64_t)rank / (uint64_t)world;
   c1 = cols * (uint64_t)(rank + 1) / (uint64_t)world;
@@ -315,6 +320,27 @@ int rcs_dist_step_local(rcs_sim** sims, int32_t world, uint64_t secs, uint32_t n
     rc = step_phase_b(s, dt, flags);
     if (rc) return rc;
   }
+  return RCS_OK;
+}
+
+int rcs_dist_set_boundaries(rcs_sim* s, int32_t world, const uint64_t* bounds) {
+  if (!s || world <= 0) return RCS_ERR_ARG;
+  if (s->strip.enabled) {
+    s->err = "strip boundaries must be set before rcs_dist_init";
+    return RCS_ERR_ARG;
+  }
+  if (!bounds) {
+    s->strip_bounds.clear();
+    return RCS_OK;
+  }
+  const uint64_t cols = strip_columns(s);
+  bool ok = bounds[0] == 0 && bounds[world] == cols;
+  for (int r = 0; r < world && ok; ++r) ok = bounds[r] < bounds[r + 1];
+  if (!ok) {
+    s->err = "strip boundaries must rise strictly from 0 to the number of cell columns";
+    return RCS_ERR_ARG;
+  }
+  s->strip_bounds.assign(bounds, bounds + world + 1);
   return RCS_OK;
 }
 

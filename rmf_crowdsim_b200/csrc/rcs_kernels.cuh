@@ -93,12 +93,22 @@ struct PackArgs {
 // strip it is appended to the send buffer of that side (both, on a very narrow strip).
 __device__ __forceinline__ void halo_pack_one(const PackArgs& pk, uint32_t i, uint32_t idx, DevStatus* status) {
   const uint32_t cx = idx / pk.nx;
+  const unsigned act = __activemask();  // the lanes that reached this call together
+  const unsigned lane = threadIdx.x & 31u;
 #pragma unroll
   for (int side = 0; side < 2; ++side) {
     const bool send = side == 0 ? (pk.has_left && cx < pk.st.c0 + pk.width) : (pk.has_right && cx + pk.width >= pk.st.c1);
-    if (!send) continue;
+    // One append per warp, not per agent: the boundary columns are contiguous in storage, so whole warps pack, and
+    // 50 000 atomics on one counter were a third of the binning pass (27 us per rank on 8 strips).
+    const unsigned m = __ballot_sync(act, send);
+    if (!m) continue;
     const HaloBuf& b = side == 0 ? pk.left : pk.right;
-    const uint32_t k = atomicAdd(b.count, 1u);
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(b.count, (unsigned)__popc(m));
+    base = __shfl_sync(act, base, leader);
+    if (!send) continue;
+    const uint32_t k = base + __popc(m & ((1u << lane) - 1u));
     if (k >= b.cap) {
       atomicAdd(&status->capacity_err, 1u);
       continue;

@@ -34,7 +34,9 @@ def strip_scene(workload: str, variant: str, rank: int, world: int, lp_none: boo
         zan = ("zanlungo", 0.1, 1.0, 0.0, 0.4, 1.0, 0.2)
     dom = float(np.ceil((side * s + 2 * margin) / cell) * cell)
     ncols = int(dom / cell)
-    c0, c1 = ncols * rank // world, ncols * (rank + 1) // world
+    # strips balanced by agent count: the crowd fills [0, side * s), the margins are empty
+    bounds = [0] + [int(round((k * side * s / world + margin) / cell)) for k in range(1, world)] + [ncols]
+    c0, c1 = bounds[rank], bounds[rank + 1]
     # lattice column i sits at x in (i*s, (i+1)*s): cell column floor((x + margin) / cell)
     i0 = max(0, int(np.floor((c0 * cell - margin) / s)) - 1)
     i1 = min(side, int(np.ceil((c1 * cell - margin) / s)) + 1)
@@ -46,6 +48,7 @@ def strip_scene(workload: str, variant: str, rank: int, world: int, lp_none: boo
     scene = SC.Scene(name=f"{workload}_{variant}_strip{rank}", width=dom, height=dom, cell=cell,
                      offset=(-margin, -margin), xy=np.zeros((0, 2)), vxy=np.zeros((0, 2)), eyesight=eyesight,
                      hl=("parity", (speed, 0.0)), lp=("none",) if lp_none else zan, seed=seed)
+    scene.meta["bounds"] = bounds
     return scene, side * side, ids, xy, vxy
 
 
@@ -73,8 +76,8 @@ def run(args) -> None:
     workload = args.workload or "c4"
     frozen = not (args.variant == "lane" and not args.no_local_plan)
     scene, n_total, ids, xy, vxy = strip_scene(workload, args.variant, rank, world, args.no_local_plan)
-    ncols = int(scene.width / scene.cell)
-    c0, c1 = ncols * rank // world, ncols * (rank + 1) // world
+    bounds = scene.meta["bounds"]
+    c0, c1 = bounds[rank], bounds[rank + 1]
     m = owned_mask(xy[:, 0], scene.offset[0], scene.cell, c0, c1)
     n_own = int(m.sum())
     # room for the owned agents, three ghost columns per side and the churn of a long committed run
@@ -82,7 +85,7 @@ def run(args) -> None:
     halo_cap = int(3.3 * per_col) + 2048  # three columns per side (W = ring + reach) and 10 % slack
     cap = int(n_own * 1.05) + 2 * halo_cap + 4096
     idx = S.LocationHash2D(scene.width, scene.height, scene.cell, scene.offset, capacity=cap, device=local)
-    sim = StripSimulation(idx, rank, world, nccl_id, halo_capacity=halo_cap)
+    sim = StripSimulation(idx, rank, world, nccl_id, halo_capacity=halo_cap, boundaries=bounds)
     assert (sim.c0, sim.c1) == (c0, c1)
     sim.add_scene_agents(scene, ids, xy, vxy)
     lib, h = sim._lib, sim._h
@@ -151,7 +154,8 @@ def run(args) -> None:
         sim.spatial_index.close()
         scene.hl = ("host", scene.hl[1])
         idx2 = S.LocationHash2D(scene.width, scene.height, scene.cell, scene.offset, capacity=cap, device=local)
-        sim2 = StripSimulation(idx2, rank, world, fresh_nccl_id(dist, torch, rank), halo_capacity=halo_cap)
+        sim2 = StripSimulation(idx2, rank, world, fresh_nccl_id(dist, torch, rank), halo_capacity=halo_cap,
+                               boundaries=bounds)
         sim2.add_scene_agents(scene, ids, xy, vxy)
         e2e = run_e2e(sim2, scene, min(K, 10), 3, dist, torch)
 
@@ -171,6 +175,7 @@ def run(args) -> None:
             "config": {
                 "workload": workload_name(workload, args.variant) + (", NoLocalPlan" if args.no_local_plan else ""),
                 "agents": n_live, "agents_per_gpu": n_live / world,
+                "strip_boundaries": "balanced by agent count (rcs_dist_set_boundaries)",
                 "parallelism": f"{world} spatial strips along x, NCCL send/recv halo (3 cell columns per side), "
                                "ring agents advanced redundantly (no migration message); the whole step, NCCL "
                                "exchange included, replays as one CUDA graph per rank",
@@ -298,7 +303,7 @@ def verify_core(dist, torch, rank: int, world: int, local: int, workload: str, v
     w_cols = 1 + int(np.floor(scene.eyesight / scene.cell)) + 1  # ring + stencil reach
     halo_cap = int(1.2 * w_cols * per_col) + 2048
     idx = S.LocationHash2D(scene.width, scene.height, scene.cell, scene.offset, capacity=n_total, device=local)
-    sim = StripSimulation(idx, rank, world, nccl_id, halo_capacity=halo_cap)
+    sim = StripSimulation(idx, rank, world, nccl_id, halo_capacity=halo_cap, boundaries=scene.meta["bounds"])
     n0 = sim.add_scene_agents(scene, ids, xy, vxy)
     for _ in range(K):
         sim.step_async(dt)

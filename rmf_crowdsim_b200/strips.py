@@ -67,9 +67,13 @@ class StripSimulation(S.Simulation):
     `nccl_unique_id()` on rank 0 and distributed by the caller (e.g. torch.distributed.broadcast)."""
 
     def __init__(self, spatial_index: S.LocationHash2D, rank: int, world: int, nccl_id: Optional[bytes],
-                 halo_capacity: int = 0):
+                 halo_capacity: int = 0, boundaries=None):
         super().__init__(spatial_index)
         self.rank, self.world = rank, world
+        if boundaries is not None:  # world + 1 cell-column boundaries instead of the equal split (every rank alike)
+            b = np.ascontiguousarray(boundaries, dtype=np.uint64)
+            assert len(b) == world + 1
+            N.check(self._h, self._lib.rcs_dist_set_boundaries(self._h, world, b.ctypes.data_as(N.c_u64p)))
         buf = None
         if world > 1:
             assert nccl_id is not None and len(nccl_id) == 128
@@ -101,7 +105,7 @@ class LocalStripGroup:
     """All ranks of a strip-partitioned simulation inside one process (single-process transport)."""
 
     def __init__(self, scene, world: int, devices: Optional[List[int]] = None, capacity: Optional[int] = None,
-                 halo_capacity: int = 0):
+                 halo_capacity: int = 0, boundaries=None):
         self.scene, self.world = scene, world
         devices = devices or [0] * world
         cap = capacity or max(scene.n, 64)
@@ -110,6 +114,10 @@ class LocalStripGroup:
             idx = S.LocationHash2D(scene.width, scene.height, scene.cell, scene.offset, capacity=cap,
                                    device=devices[r])
             self.sims.append(S.Simulation(idx))
+            if boundaries is not None:
+                b = np.ascontiguousarray(boundaries, dtype=np.uint64)
+                N.check(self.sims[-1]._h, self.sims[-1]._lib.rcs_dist_set_boundaries(self.sims[-1]._h, world,
+                                                                                     b.ctypes.data_as(N.c_u64p)))
         self._lib = self.sims[0]._lib
         self._handles = (C.c_void_p * world)(*[s._h for s in self.sims])
         rc = self._lib.rcs_dist_init_local(self._handles, world, int(halo_capacity))

@@ -277,3 +277,23 @@ def test_source_sink_next_to_a_strip_boundary_is_refused():
         grp.add_source_sink(make(32.2))  # column 16 is rank 1's first: the 0.4 m probe reaches into column 15
     grp.add_source_sink(make(33.0))      # probe columns 16..16
     grp.add_source_sink(make(0.1))       # the domain's edge is nobody's boundary
+
+
+def test_caller_supplied_strip_boundaries_match_one_handle():
+    """rcs_dist_set_boundaries: strips balanced by agent count instead of equal column counts (the crowd does not fill
+    the grid) give the single handle's bits as well; bad boundaries are refused."""
+    scene = SC.uniform_crowd(48, "lane", margin=16.0, seed=9)  # 80 m domain, 40 columns, agents in columns 8..31
+    single = SC.build_simulation(scene)
+    bounds = [0, 16, 24, 40]
+    grp = LocalStripGroup(scene, 3, capacity=scene.n, halo_capacity=2048, boundaries=bounds)
+    assert [strip_columns(sm, r, 3) for r, sm in enumerate(grp.sims)] == [(0, 16), (16, 24), (24, 40)]
+    dt = R.Duration(0, 200_000_000)
+    for _ in range(12):
+        single.step(dt)
+        grp.step(dt)
+    sa, sb = single.read_state(), grp.read_state()
+    assert np.array_equal(sa["id"], sb["id"])
+    for k in ("x", "y", "vx", "vy"):
+        assert np.array_equal(sa[k].view(np.uint64), sb[k].view(np.uint64)), k
+    with pytest.raises(R.CrowdsimError):
+        LocalStripGroup(scene, 3, capacity=scene.n, halo_capacity=2048, boundaries=[0, 24, 16, 40])
