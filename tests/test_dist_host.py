@@ -29,7 +29,9 @@ def _worker(rank: int, world: int, port: int, variant: str, q):
     try:
         scene, n_total, ids, xy, vxy = DB.strip_scene("side64", variant, rank, world, lp_none=False)
         ncols = int(scene.width / scene.cell)
-        c0, c1 = ncols * rank // world, ncols * (rank + 1) // world
+        bounds = scene.meta["bounds"]  # strips balanced by agent count (rcs_dist_set_boundaries)
+        assert bounds[0] == 0 and bounds[-1] == ncols and len(bounds) == world + 1
+        c0, c1 = bounds[rank], bounds[rank + 1]
         m = owned_mask(xy[:, 0], scene.offset[0], scene.cell, c0, c1)
         # every agent of the global crowd is owned by exactly one rank
         t = torch.tensor([float(m.sum()), float(ids[m].astype(np.float64).sum())], dtype=torch.float64)
