@@ -106,7 +106,9 @@ int rcs_hl_host(rcs_sim* sim, uint32_t* out_hl);
  * the caller (xy = n_points interleaved x,y): the reference plans it with the third-party `mapf` crate
  * (rmf/mod.rs:160-192), which is host-side graph search and out of scope.  Agents enter the cache at route
  * point 0 through HighLevelPlanner::set_target: automatically when a SourceSink spawns them (lib.rs:242-249)
- * and whenever they reach one of its waypoints (lib.rs:326-333), or explicitly with rcs_hl_route_set_target. */
+ * and whenever they reach one of its waypoints (lib.rs:326-333), or explicitly with rcs_hl_route_set_target.
+ * A SourceSink with a route planner takes exactly ONE waypoint, the sink (the reference plans a new route per waypoint;
+ * here a planner is one polyline): rcs_add_source_sink refuses more with RCS_ERR_ARG. */
 int rcs_hl_route(rcs_sim* sim, uint64_t n_points, const double* xy, uint32_t* out_hl);
 int rcs_hl_route_set_target(rcs_sim* sim, uint64_t n, const uint64_t* ids);
 int rcs_hl_none(rcs_sim* sim, uint32_t* out_hl);
@@ -283,7 +285,8 @@ int rcs_dist_strip(rcs_sim* sim, int32_t rank, int32_t world, uint64_t* c0, uint
 /* add_agents with caller-supplied global ids (the global sequential allocation of lib.rs:128-129
  * is done by the host program across ranks) and initial velocities (vxy may be NULL).  Ghosts carry the number of
  * their (high-level planner, local planner, eyesight) group: EVERY rank makes the same calls in the same order, with
- * n = 0 where none of the batch lies in its strip, so that the group tables agree. */
+ * n = 0 where none of the batch lies in its strip, so that the group tables agree.  Ids must be < 2^32 (the id -> slot
+ * tables are dense over the id range). */
 int rcs_dist_add_agents(rcs_sim* sim, uint64_t n, const uint64_t* ids, const double* xy, const double* vxy,
                         uint32_t hl, uint32_t lp, double eyesight);
 /* Single-process transport: sims[r] is rank r of `world` handles that live in this process (on one

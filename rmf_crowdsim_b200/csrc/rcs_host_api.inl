@@ -263,6 +263,15 @@ static int add_agents_impl(rcs_sim* s, uint64_t n, const uint64_t* ids, const do
       }
     }
   }
+  if (ids) {
+    // id -> slot tables are dense arrays over the id range (12 bytes per id up to the largest one)
+    for (uint64_t k = 0; k < n; ++k) {
+      if (ids[k] >> 32) {
+        s->err = "caller-supplied agent ids must be < 2^32";
+        return RCS_ERR_ARG;
+      }
+    }
+  }
   if (n == 0) {
     // strips: ghosts carry their group number, so every rank must hold the same group table in the same order --
     // also a rank whose strip is empty at this moment

@@ -146,8 +146,20 @@ int rcs_index_add_or_update(rcs_sim* s, uint64_t n, const uint64_t* ids, const d
   // split into updates of known ids and inserts of new ones (location_hash_2d.rs:134-145)
   rc = build_slot_table(s);
   if (rc) return rc;
-  std::vector<uint32_t> slots(std::max<uint64_t>(s->max_id_plus1, 1));
-  CU_TRY(s, cudaMemcpy(slots.data(), s->slot_of_id, slots.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  // the slots of the n ids only (the table itself stays on the device: one agent at a time must not cost O(max id))
+  std::vector<uint32_t> slots(n);
+  {
+    rc = ensure_stage(s, n * 12);
+    if (rc) return rc;
+    uint64_t* d_ids = static_cast<uint64_t*>(s->stage);
+    uint32_t* d_slots = reinterpret_cast<uint32_t*>(static_cast<char*>(s->stage) + n * 8);
+    CU_TRY(s, cudaMemcpyAsync(d_ids, ids, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
+    lookup_slots_kernel<<<blocks_for(n, 256), 256, 0, s->stream>>>((uint32_t)n, d_ids, s->slot_of_id,
+                                                                   std::max<uint64_t>(s->max_id_plus1, 1), d_slots);
+    s->launches += 1;
+    CU_TRY(s, cudaMemcpyAsync(slots.data(), d_slots, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(s, cudaStreamSynchronize(s->stream));
+  }
   std::vector<uint64_t> upd_ids, new_ids;
   std::vector<double> ux, uy, nxy;
   for (uint64_t k = 0; k < n; ++k) {
@@ -160,7 +172,7 @@ int rcs_index_add_or_update(rcs_sim* s, uint64_t n, const uint64_t* ids, const d
       s->err = "Index out of bounds";
       return RCS_ERR_OUT_OF_BOUNDS;
     }
-    bool known = ids[k] < s->max_id_plus1 && slots[ids[k]] != 0xffffffffu;
+    bool known = slots[k] != 0xffffffffu;
     // an id inserted earlier in this very call counts as known for later entries
     if (!known) {
       auto it = std::find(new_ids.begin(), new_ids.end(), ids[k]);

@@ -537,6 +537,12 @@ int rcs_add_source_sink(rcs_sim* s, const rcs_source_sink_desc* d, uint64_t* out
     s->err = "a source sink needs at least one waypoint (the reference indexes waypoints[0], lib.rs:244)";
     return RCS_ERR_ARG;
   }
+  if (s->hls[d->hl].kind == HL_ROUTE && d->n_waypoints > 1) {
+    // RMFPlanner::set_target plans a new route to every waypoint (rmf/mod.rs:217-237); the device-side follower has
+    // one caller-supplied polyline per planner, so it can serve the leg to the sink only
+    s->err = "a route-follower source sink takes exactly one waypoint (the sink): one polyline per planner";
+    return RCS_ERR_ARG;
+  }
   uint64_t idx;
   if (!host_location_to_index(s->grid, d->source_x, d->source_y, idx)) {
     // the reference fails at the first spawn (lib.rs:146-149 -> :252); reported when the source is added

@@ -1162,6 +1162,15 @@ __global__ void build_slot_of_id_kernel(uint32_t n, const uint64_t* __restrict__
   if (v < table_len) slot_of_id[v] = i;
 }
 
+// out[k] = slot of id ids[k], 0xffffffff if it is not live (the id -> slot table stays on the device)
+__global__ void lookup_slots_kernel(uint32_t n, const uint64_t* __restrict__ ids, const uint32_t* __restrict__ slot_of_id,
+                                    uint64_t table_len, uint32_t* __restrict__ out) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint64_t v = ids[k];
+  out[k] = v < table_len ? slot_of_id[v] : 0xffffffffu;
+}
+
 // largest live id (strips: agents migrate in with ids this handle never allocated)
 __global__ void max_id_kernel(uint32_t n, const uint64_t* __restrict__ id, unsigned long long* out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

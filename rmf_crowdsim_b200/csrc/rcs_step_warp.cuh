@@ -380,6 +380,7 @@ __global__ void __launch_bounds__(32 * SW_WARPS, 6) step_warp_kernel(StepArgs a)
       fast = coop && (sl.w >> 24) != 0u && l0 <= SW_SLICE_MAX && l1 <= SW_SLICE_MAX && l2 <= SW_SLICE_MAX;
       if (!fast) {
         l0 = l1 = l2 = 0;
+        thr2 = 0.0;  // the filter's padding reads of this lane must reject everything (it takes no part)
         active = false;
         zan = false;
         aside = coop ? 1u : 2u;

@@ -172,22 +172,27 @@ def test_monotonic_crowd_rounding():
 def test_route_follower_on_the_device_matches_oracle():
     """the per-step half of RMFPlanner (rmf/mod.rs:197-215) -- unit velocity towards
     the current route point, advance within 0.1 m -- with routes supplied as polylines, spawned by source sinks
-    whose coarse waypoints send the agents back to the head of the route (set_target, lib.rs:326-333)."""
+    (set_target at spawn, lib.rs:242-249) whose single waypoint is the sink."""
     w = h = 64.0
     off = (-32.0, -32.0)
     o = O.OracleSim(w, h, 2.0, off)
     g = R.Simulation(R.LocationHash2D(w, h, 2.0, off, capacity=2048))
     keep = []
     routes = [
-        ((-20.0, -10.0), [(-10.0, -10.0), (-10.0, 0.0), (5.0, 0.0), (20.0, 10.0)], [(-10.0, 0.0), (20.0, 10.0)]),
+        ((-20.0, -10.0), [(-10.0, -10.0), (-10.0, 0.0), (5.0, 0.0), (20.0, 10.0)], [(20.0, 10.0)]),
         ((20.0, 12.0), [(10.0, 12.0), (0.0, 5.0), (-15.0, 5.0)], [(-15.0, 5.0)]),
-        ((0.0, -25.0), [(0.0, -12.0), (3.0, -2.0), (0.0, 20.0)], [(3.0, -2.0), (0.0, 20.0)]),
+        ((0.0, -25.0), [(0.0, -12.0), (3.0, -2.0), (0.0, 20.0)], [(0.0, 20.0)]),
     ]
     for src, route, wps in routes:
         o.add_source_sink(src, 0.6, 2.0, o.hl_route(route), o.lp_none(), wps, False, 2.0)
         hl, lp = R.RouteFollowPlan(route), R.NoLocalPlan()
         keep.append((hl, lp))
         g.add_source_sink(R.SourceSink(src, 0.6, R.MonotonicCrowd(2.0), hl, lp, wps, False, 2.0))
+    # one polyline per planner: a route-follower source sink with intermediate waypoints (for which the reference
+    # plans a new route each, rmf/mod.rs:217-237) is refused
+    with pytest.raises(R.CrowdsimError):
+        g.add_source_sink(R.SourceSink((5.0, 25.0), 0.6, R.MonotonicCrowd(2.0), R.RouteFollowPlan([(9.0, 25.0), (15.0, 25.0)]),
+                                       R.NoLocalPlan(), [(9.0, 25.0), (15.0, 25.0)], False, 2.0))
     destroyed = 0
     for step in range(150):
         if o.agent_count():
