@@ -280,6 +280,16 @@ int rcs_dist_init(rcs_sim* sim, int32_t rank, int32_t world, const uint8_t nccl_
  * rising strictly from 0 to the number of cell columns) instead of the equal split -- e.g. balanced by agent count
  * when the crowd does not fill the grid.  bounds == NULL: back to the equal split. */
 int rcs_dist_set_boundaries(rcs_sim* sim, int32_t world, const uint64_t* bounds);
+/* Optional, after rcs_dist_init on a multi-process job in which every rank has its own GPU: the peer-store halo
+ * transport.  rcs_dist_peer_export returns the CUDA IPC handle (64 bytes) of this rank's receive arena; the host
+ * program distributes the handles (e.g. torch.distributed.all_gather) and gives every rank its two neighbours'
+ * (NULL where there is none) with rcs_dist_peer_connect.  From then on the binning pass stores the boundary columns
+ * straight into the neighbour's memory over NVLink and a one-block kernel releases the round number the neighbour's
+ * unpack kernel waits for (at most 30 s, then the step fails): no ncclSend / ncclRecv in the step, and a steady-state
+ * step replays as one CUDA graph.  Every rank of the job must connect before the next step.  NCCL stays in use for
+ * the spawn-set all-reduce of source sinks. */
+int rcs_dist_peer_export(rcs_sim* sim, uint8_t out_handle[64]);
+int rcs_dist_peer_connect(rcs_sim* sim, const uint8_t* left_handle, const uint8_t* right_handle);
 /* Column range [c0, c1) owned by `rank` of `world` for this handle's grid. */
 int rcs_dist_strip(rcs_sim* sim, int32_t rank, int32_t world, uint64_t* c0, uint64_t* c1);
 /* add_agents with caller-supplied global ids (the global sequential allocation of lib.rs:128-129

@@ -54,6 +54,23 @@ struct HaloMem {
   HaloBuf buf{};
 };
 
+// Peer-store halo transport (rcs_dist_peer_export / rcs_dist_peer_connect): this rank's receive arena, which the
+// neighbours map through CUDA IPC and store into, and the mappings of theirs.
+// Arena: [64 B: magic, cap][64 B header left side][64 B header right side][rows left side][rows right side]; a header
+// is two halves of [count, failed, round, pad]; the rows of a side are pos, vel, id, meta, pv with 2 x cap entries
+// each (two halves, used in turn).
+struct PeerHalo {
+  bool enabled = false;
+  void* arena = nullptr;
+  uint64_t arena_bytes = 0;
+  uint32_t cap = 0;
+  void* nb_arena[2] = {nullptr, nullptr};   // [0] left neighbour's arena, [1] right neighbour's
+  HaloBuf remote[2]{};                       // where this rank's left / right boundary columns go
+  uint32_t* remote_hdr[2] = {nullptr, nullptr};
+  HaloBuf local[2]{};                        // what the left / right neighbour stores into
+  uint32_t* xseq = nullptr;                  // device: exchange round, bumped by begin_step_kernel
+};
+
 // NCCL entry points, resolved with dlopen at rcs_dist_init (the library itself does not link NCCL, so it
 // loads on boxes without it and single-GPU use never touches it).
 struct Id128 {
@@ -192,6 +209,7 @@ struct rcs_sim {
   uint32_t halo_width = 0;  // columns sent to each neighbour = ring h + stencil reach q
   std::vector<uint64_t> strip_bounds;  // optional: world + 1 column boundaries (rcs_dist_set_boundaries); empty = equal split
   rcs_host::HaloMem send_l, send_r, recv_l, recv_r;
+  rcs_host::PeerHalo peer;
   void* nccl_comm = nullptr;
   std::vector<rcs_sim*> local_group;  // single-process transport: the handles of all ranks, by rank
   cudaEvent_t ev_packed = nullptr, ev_copied = nullptr;

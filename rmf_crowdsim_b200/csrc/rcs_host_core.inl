@@ -203,6 +203,13 @@ static int bin_agents(rcs_sim* s, uint32_t n_ub, const uint32_t* first, uint32_t
     pk.left = s->send_l.buf;
     pk.right = s->send_r.buf;
     pk.cur = s->cur;
+    if (s->peer.enabled) {  // rows go straight into the neighbours' receive buffers; the counts stay local
+      pk.left = s->peer.remote[0];
+      pk.right = s->peer.remote[1];
+      pk.left.count = s->send_l.buf.count;
+      pk.right.count = s->send_r.buf.count;
+      pk.xseq = s->peer.xseq;
+    }
   }
   if (pack_only) {  // the owned agents were binned by the previous step's epilogue
     halo_pack_kernel<<<blocks_for(launch_n, 256), 256, 0, s->stream>>>(n_ub, s->cnt + CNT_TOT, s->cellid, pk, s->d_status);

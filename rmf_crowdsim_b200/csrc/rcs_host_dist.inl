@@ -186,7 +186,7 @@ static int step_spawn_set_nccl(rcs_sim* s) {
 }
 
 static int step_exchange_nccl(rcs_sim* s) {
-  if (s->world == 1) return RCS_OK;
+  if (s->world == 1 || s->peer.enabled) return RCS_OK;  // peer stores: halo_publish_kernel was the exchange
   if (!s->nccl_comm) {
     s->err = "strip handle has no communicator";
     return RCS_ERR_NCCL;
@@ -205,10 +205,44 @@ static int step_exchange_nccl(rcs_sim* s) {
   return RCS_OK;
 }
 
+// ---- peer-store transport ----------------------------------------------------------------------------------------
+constexpr uint32_t PEER_MAGIC = 0x52435348u;  // "RCSH"
+constexpr uint64_t PEER_ROW_BYTES = 64;       // pos 16 + vel 16 + id 8 + meta 8 + pv 16
+
+static uint64_t peer_arena_bytes(uint32_t cap) { return 192 + 2ull * 2ull * cap * PEER_ROW_BYTES; }
+
+// the receive buffer of one side (0: from the left neighbour, 1: from the right one) inside an arena
+static HaloBuf peer_side(void* arena, uint32_t cap, int side, uint32_t** hdr) {
+  char* p = static_cast<char*>(arena);
+  *hdr = reinterpret_cast<uint32_t*>(p + 64 + 64 * side);
+  char* rows = p + 192 + (uint64_t)side * 2ull * cap * PEER_ROW_BYTES;
+  HaloBuf b{};
+  b.count = *hdr;
+  b.cap = cap;
+  const uint64_t n = 2ull * cap;  // two halves
+  b.pos = reinterpret_cast<double2*>(rows);
+  b.vel = reinterpret_cast<double2*>(rows + 16 * n);
+  b.id = reinterpret_cast<unsigned long long*>(rows + 32 * n);
+  b.meta = reinterpret_cast<unsigned long long*>(rows + 40 * n);
+  b.pv = reinterpret_cast<double2*>(rows + 48 * n);
+  return b;
+}
+
+static void peer_teardown(rcs_sim* s) {
+  for (void*& m : s->peer.nb_arena) {
+    if (m) cudaIpcCloseMemHandle(m);
+    m = nullptr;
+  }
+  cudaFree(s->peer.arena);
+  cudaFree(s->peer.xseq);
+  s->peer = PeerHalo{};
+}
+
 }  // namespace rcs_host
 
 static void dist_teardown(rcs_sim* s) {
   using namespace rcs_host;
+  peer_teardown(s);
   if (s->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->nccl_comm);
   s->nccl_comm = nullptr;
   halo_free(s->send_l);
@@ -320,6 +354,78 @@ int rcs_dist_step_local(rcs_sim** sims, int32_t world, uint64_t secs, uint32_t n
     rc = step_phase_b(s, dt, flags);
     if (rc) return rc;
   }
+  return RCS_OK;
+}
+
+int rcs_dist_peer_export(rcs_sim* s, uint8_t out_handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!s || !out_handle) return RCS_ERR_ARG;
+  CU_TRY(s, cudaSetDevice(s->device));
+  if (!s->strip.enabled || s->world < 2 || !s->local_group.empty()) {
+    s->err = "the peer-store transport is for strip handles of a multi-process job (one GPU per rank)";
+    return RCS_ERR_ARG;
+  }
+  int rc = do_sync(s);
+  if (rc) return rc;
+  if (!s->peer.arena) {
+    const uint32_t cap = s->recv_l.buf.cap;
+    const uint64_t bytes = peer_arena_bytes(cap);
+    CU_TRY(s, cudaMalloc(&s->peer.arena, bytes));
+    CU_TRY(s, cudaMemset(s->peer.arena, 0, bytes));
+    const uint32_t desc[2] = {PEER_MAGIC, cap};
+    CU_TRY(s, cudaMemcpy(s->peer.arena, desc, sizeof(desc), cudaMemcpyHostToDevice));
+    CU_TRY(s, dalloc(&s->peer.xseq, 1));
+    CU_TRY(s, cudaMemset(s->peer.xseq, 0, sizeof(uint32_t)));
+    CU_TRY(s, cudaDeviceSynchronize());  // zeroed before any neighbour can see it
+    s->peer.arena_bytes = bytes;
+    s->peer.cap = cap;
+    uint32_t* hdr = nullptr;
+    s->peer.local[0] = peer_side(s->peer.arena, cap, 0, &hdr);
+    s->peer.local[1] = peer_side(s->peer.arena, cap, 1, &hdr);
+  }
+  cudaIpcMemHandle_t h;
+  CU_TRY(s, cudaIpcGetMemHandle(&h, s->peer.arena));
+  std::memcpy(out_handle, &h, 64);
+  return RCS_OK;
+}
+
+int rcs_dist_peer_connect(rcs_sim* s, const uint8_t* left_handle, const uint8_t* right_handle) {
+  if (!s) return RCS_ERR_ARG;
+  CU_TRY(s, cudaSetDevice(s->device));
+  if (!s->peer.arena || s->peer.enabled) {
+    s->err = "rcs_dist_peer_connect follows rcs_dist_peer_export, once";
+    return RCS_ERR_ARG;
+  }
+  const bool has[2] = {s->rank > 0, s->rank + 1 < s->world};
+  const uint8_t* hs[2] = {left_handle, right_handle};
+  if ((has[0] && !left_handle) || (has[1] && !right_handle)) {
+    s->err = "a neighbour's handle is missing";
+    return RCS_ERR_ARG;
+  }
+  int rc = do_sync(s);
+  if (rc) return rc;
+  for (int side = 0; side < 2; ++side) {
+    if (!has[side]) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, hs[side], 64);
+    cudaError_t e = cudaIpcOpenMemHandle(&s->peer.nb_arena[side], h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      s->err = std::string("CUDA error: ") + cudaGetErrorString(e) + " at cudaIpcOpenMemHandle (peer-store transport)";
+      peer_teardown(s);
+      return RCS_ERR_CUDA;
+    }
+    uint32_t desc[2] = {0, 0};
+    e = cudaMemcpy(desc, s->peer.nb_arena[side], sizeof(desc), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess || desc[0] != PEER_MAGIC || desc[1] == 0) {
+      s->err = "the neighbour's receive arena cannot be read (no peer access between the two GPUs?)";
+      peer_teardown(s);
+      return RCS_ERR_CUDA;
+    }
+    // this rank's LEFT boundary columns are what the left neighbour receives from its RIGHT side, and vice versa
+    s->peer.remote[side] = peer_side(s->peer.nb_arena[side], desc[1], 1 - side, &s->peer.remote_hdr[side]);
+  }
+  s->peer.enabled = true;
+  s->graph_epoch += 1;
   return RCS_OK;
 }
 

@@ -69,7 +69,7 @@ int rcs_step_in_loop(rcs_sim* s, uint64_t secs, uint32_t nanos, const uint64_t* 
   inloop_rank_kernel<<<blocks_for(n, 256), 256, 0, s->stream>>>(n, s->srt.id, d_pos_of_id, L, m.rank);
   s->launches += 1;
 
-  begin_step_kernel<<<1, 1, 0, s->stream>>>(s->d_status, s->cnt, nullptr, nullptr);
+  begin_step_kernel<<<1, 1, 0, s->stream>>>(s->d_status, s->cnt, nullptr, nullptr, nullptr);
   s->launches += 1;
   const double dt = (double)secs + (double)nanos / 1e9;  // Duration::as_secs_f64
   InLoopArgs q{};

@@ -187,7 +187,8 @@ static int step_phase_a1(rcs_sim* s, double dt) {
     if (nb && nb != s && std::abs(nb->rank - s->rank) == 1 && nb->ev_copied)
       CU_TRY(s, cudaStreamWaitEvent(s->stream, nb->ev_copied, 0));
   begin_step_kernel<<<1, 1, 0, s->stream>>>(s->d_status, s->cnt, s->strip.enabled ? s->send_l.buf.count : nullptr,
-                                            s->strip.enabled ? s->send_r.buf.count : nullptr);
+                                            s->strip.enabled ? s->send_r.buf.count : nullptr,
+                                            s->peer.enabled ? s->peer.xseq : nullptr);
   s->launches += 1;
   if (s->n_sources_alive) {
     const uint32_t n_before = s->strip.enabled ? (uint32_t)s->cap : s->n_ub;
@@ -237,6 +238,11 @@ static int step_phase_a2(rcs_sim* s, double dt) {
     }
     if (rc) return rc;
     if (s->ev_packed) CU_TRY(s, cudaEventRecord(s->ev_packed, s->stream));
+    if (s->peer.enabled) {  // the exchange: count, failed flag and the round number, behind the rows of the pack pass
+      halo_publish_kernel<<<1, 32, 0, s->stream>>>(s->peer.xseq, s->send_l.buf.count, s->send_r.buf.count,
+                                                   s->peer.remote_hdr[0], s->peer.remote_hdr[1]);
+      s->launches += 1;
+    }
   }
   CU_TRY(s, cudaGetLastError());
   return RCS_OK;
@@ -279,9 +285,12 @@ static int step_phase_b(rcs_sim* s, double dt, uint32_t flags) {
   if (n_ub && sorted_path(s)) {
     if (s->strip.enabled) {
       const int has_l = s->rank > 0, has_r = s->rank + 1 < s->world;
-      const uint32_t ghosts_ub = s->recv_l.buf.cap + s->recv_r.buf.cap;
+      const HaloBuf& rl = s->peer.enabled ? s->peer.local[0] : s->recv_l.buf;
+      const HaloBuf& rr = s->peer.enabled ? s->peer.local[1] : s->recv_r.buf;
+      const uint32_t ghosts_ub = rl.cap + rr.cap;
       halo_unpack_kernel<<<blocks_for(ghosts_ub, 256), 256, 0, s->stream>>>(
-          s->cur, s->keep, (uint32_t)s->cap, s->recv_l.buf, s->recv_r.buf, has_l, has_r, s->cnt, s->d_status);
+          s->cur, s->keep, (uint32_t)s->cap, rl, rr, has_l, has_r, s->cnt, s->d_status,
+          s->peer.enabled ? s->peer.xseq : nullptr);
       s->launches += 1;
       rc = bin_agents(s, n_ub, s->cnt + CNT_CUR, ghosts_ub);
     } else if (!s->binned_ahead) {
@@ -438,7 +447,10 @@ int rcs_step_async(rcs_sim* s, uint64_t secs, uint32_t nanos, uint32_t flags) {
   // Between processes the NCCL exchange stays outside the graph: captured send / recv pairs were measured 3 x slower
   // than eager ones on 8 ranks (1.85 against 0.59 ms per step; on 2 ranks there is no difference).  Phase A and the
   // exchange are then enqueued kernel by kernel and only phase B -- the rebuild and the step kernels -- replays.
-  const bool from_b = steady && s->strip.enabled && s->world > 1;
+  // With the peer-store transport (rcs_dist_peer_connect) the exchange is kernels of this library: the whole step is
+  // captured, as on a single handle -- unless source sinks need the spawn-set all-reduce of phase A.
+  const bool nccl_in_step = !s->peer.enabled || s->n_sources_alive != 0;
+  const bool from_b = steady && s->strip.enabled && s->world > 1 && nccl_in_step;
   if (from_b) {
     int rc = step_phase_a(s, dt);
     if (rc) return rc;

@@ -87,6 +87,7 @@ struct PackArgs {
   StripDev st;
   HaloBuf left, right;
   AgentArrays cur;
+  const uint32_t* xseq;  // peer-store transport: exchange round (its parity picks the half of the neighbour's buffer)
 };
 
 // Strips: agent i of the owned agents sits in cell `idx`; if that is one of the outermost `width` columns of the
@@ -95,6 +96,7 @@ __device__ __forceinline__ void halo_pack_one(const PackArgs& pk, uint32_t i, ui
   const uint32_t cx = idx / pk.nx;
   const unsigned act = __activemask();  // the lanes that reached this call together
   const unsigned lane = threadIdx.x & 31u;
+  const uint32_t par = pk.xseq ? (*pk.xseq & 1u) : 0u;
 #pragma unroll
   for (int side = 0; side < 2; ++side) {
     const bool send = side == 0 ? (pk.has_left && cx < pk.st.c0 + pk.width) : (pk.has_right && cx + pk.width >= pk.st.c1);
@@ -108,11 +110,12 @@ __device__ __forceinline__ void halo_pack_one(const PackArgs& pk, uint32_t i, ui
     if ((int)lane == leader) base = atomicAdd(b.count, (unsigned)__popc(m));
     base = __shfl_sync(act, base, leader);
     if (!send) continue;
-    const uint32_t k = base + __popc(m & ((1u << lane) - 1u));
+    uint32_t k = base + __popc(m & ((1u << lane) - 1u));
     if (k >= b.cap) {
       atomicAdd(&status->capacity_err, 1u);
       continue;
     }
+    k += par * b.cap;  // peer-store transport: the rows go straight into the neighbour's receive buffer
     b.pos[k] = pk.cur.pos[i];
     b.vel[k] = pk.cur.vel[i];
     b.id[k] = pk.cur.id[i];
@@ -1281,7 +1284,9 @@ __global__ void fill_f64_kernel(uint64_t n, double* p, double v) {
 // ---------------------------------------------------------------------------------------------
 // strips: also resets the headers of the two send buffers: [0] = number of packed agents, [1] = "this rank has
 // failed" (so that a failure reaches the neighbours with the next exchange and the whole job stops within `world` steps)
-__global__ void begin_step_kernel(DevStatus* st, uint32_t* cnt, uint32_t* send_l_hdr, uint32_t* send_r_hdr) {
+__global__ void begin_step_kernel(DevStatus* st, uint32_t* cnt, uint32_t* send_l_hdr, uint32_t* send_r_hdr,
+                                  uint32_t* xseq) {
+  if (xseq) *xseq += 1u;  // peer-store transport: one exchange round per step, failed steps included
   if (send_l_hdr) {
     send_l_hdr[0] = 0u;
     send_r_hdr[0] = 0u;
@@ -1508,15 +1513,86 @@ __global__ void ss_spawn_kernel(GridDev g, const SourceSinkDev* __restrict__ ss,
 // each array `cap` entries.  Packed order is arbitrary (atomic append); the receiver re-sorts.
 // ---------------------------------------------------------------------------------------------
 // appends the ghosts of both received buffers after the owned agents; cnt[CNT_TOT] = owned + ghosts
+// ---- peer-store transport (one process per GPU, every GPU its own) ----------------------------------------------
+// The pack pass stores the boundary rows straight into the neighbour's receive buffer over NVLink (rcs_dist_peer_*:
+// the buffers are CUDA IPC mappings), halo_publish_kernel then writes count + failed flag and releases the round
+// number; the neighbour's halo_unpack_kernel acquires it.  Receive buffers have two halves used in turn: a rank
+// cannot publish round k + 2 before it has unpacked round k + 1, which its neighbour published after unpacking
+// round k -- so the half being written is never one still being read.
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// header of one half of a receive buffer: [count, failed, round, pad]
+__global__ void halo_publish_kernel(const uint32_t* __restrict__ xseq, const uint32_t* __restrict__ send_l_hdr,
+                                    const uint32_t* __restrict__ send_r_hdr, uint32_t* remote_l_hdr,
+                                    uint32_t* remote_r_hdr) {
+  const uint32_t seq = *xseq, par = seq & 1u;
+  const uint32_t* src = threadIdx.x == 0 ? send_l_hdr : send_r_hdr;
+  uint32_t* dst = threadIdx.x == 0 ? remote_l_hdr : remote_r_hdr;
+  if (threadIdx.x > 1 || !dst) return;
+  dst += 4u * par;
+  dst[0] = src[0];
+  dst[1] = src[1];
+  // the rows were stored by the kernel before this one; the fence orders them (and the two words above) before the
+  // round number for an observer on the other GPU
+  __threadfence_system();
+  st_release_sys(dst + 2, seq);
+}
+
+constexpr unsigned long long HALO_WAIT_NS = 30ull * 1000000000ull;
+
 __global__ void halo_unpack_kernel(AgentArrays cur, uint32_t* __restrict__ keep, uint32_t cap, HaloBuf left,
-                                   HaloBuf right, int has_left, int has_right, uint32_t* cnt, DevStatus* status) {
+                                   HaloBuf right, int has_left, int has_right, uint32_t* cnt, DevStatus* status,
+                                   const uint32_t* __restrict__ xseq) {
+  uint32_t par = 0u;
+  if (xseq) {
+    // wait for both neighbours' rounds (another GPU's kernel releases them; bounded, so a dead peer fails the step
+    // instead of hanging the device)
+    __shared__ uint32_t s_ok;
+    const uint32_t seq = *xseq;
+    par = seq & 1u;
+    if (threadIdx.x == 0) {
+      const unsigned long long t0 = global_timer_ns();
+      uint32_t ok = 1u;
+      for (int side = 0; side < 2 && ok; ++side) {
+        if (!(side == 0 ? has_left : has_right)) continue;
+        const uint32_t* flag = (side == 0 ? left.count : right.count) + 4u * par + 2u;
+        while ((int32_t)(ld_acquire_sys(flag) - seq) < 0) {
+          __nanosleep(64);
+          if (global_timer_ns() - t0 > HALO_WAIT_NS) {
+            ok = 0u;
+            break;
+          }
+        }
+      }
+      s_ok = ok;
+    }
+    __syncthreads();
+    if (!s_ok) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) status->failed = 1;  // reported as "a neighbouring rank failed"
+      return;
+    }
+  }
   if (status->failed) return;
-  if ((has_left && left.count[1]) || (has_right && right.count[1])) {
+  const uint32_t* lh = left.count + 4u * par;
+  const uint32_t* rh = right.count + 4u * par;
+  if ((has_left && __ldcg(lh + 1)) || (has_right && __ldcg(rh + 1))) {
     if (blockIdx.x == 0 && threadIdx.x == 0) status->failed = 1;  // a neighbour failed: stop here too
     return;
   }
   const uint32_t n0 = cnt[CNT_CUR];
-  uint32_t nl = has_left ? left.count[0] : 0u, nr = has_right ? right.count[0] : 0u;
+  uint32_t nl = has_left ? __ldcg(lh) : 0u, nr = has_right ? __ldcg(rh) : 0u;
   if (nl > left.cap) nl = left.cap;
   if (nr > right.cap) nr = right.cap;
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1530,16 +1606,18 @@ __global__ void halo_unpack_kernel(AgentArrays cur, uint32_t* __restrict__ keep,
   }
   if (k >= nl + nr) return;
   const HaloBuf& b = k < nl ? left : right;
-  const uint32_t e = k < nl ? k : k - nl;
+  const uint32_t e = (k < nl ? k : k - nl) + par * b.cap;
   const uint32_t slot = n0 + k;
   if (slot >= cap) return;
-  cur.pos[slot] = b.pos[e];
-  cur.vel[slot] = b.vel[e];
-  cur.id[slot] = b.id[e];
-  cur.grp[slot] = (uint32_t)(b.meta[e] & 0xffffffffull);
-  cur.wp[slot] = (uint32_t)(b.meta[e] >> 32);
+  // (L1 is not coherent with another GPU's stores: the rows are read at L2)
+  cur.pos[slot] = __ldcg(b.pos + e);
+  cur.vel[slot] = __ldcg(b.vel + e);
+  cur.id[slot] = __ldcg(b.id + e);
+  const unsigned long long meta = __ldcg(b.meta + e);
+  cur.grp[slot] = (uint32_t)(meta & 0xffffffffull);
+  cur.wp[slot] = (uint32_t)(meta >> 32);
   keep[slot] = 1u;
-  if (cur.pv) cur.pv[slot] = b.pv[e];
+  if (cur.pv) cur.pv[slot] = __ldcg(b.pv + e);
 }
 
 // FP64 pipe peak: independent DFMA / DADD chains.

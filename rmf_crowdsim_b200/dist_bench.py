@@ -85,7 +85,8 @@ def run(args) -> None:
     halo_cap = int(3.3 * per_col) + 2048  # three columns per side (W = ring + reach) and 10 % slack
     cap = int(n_own * 1.05) + 2 * halo_cap + 4096
     idx = S.LocationHash2D(scene.width, scene.height, scene.cell, scene.offset, capacity=cap, device=local)
-    sim = StripSimulation(idx, rank, world, nccl_id, halo_capacity=halo_cap, boundaries=bounds)
+    sim = StripSimulation(idx, rank, world, nccl_id, halo_capacity=halo_cap, boundaries=bounds,
+                          peer_gather=peer_gather(dist, torch))
     assert (sim.c0, sim.c1) == (c0, c1)
     sim.add_scene_agents(scene, ids, xy, vxy)
     lib, h = sim._lib, sim._h
@@ -155,7 +156,7 @@ def run(args) -> None:
         scene.hl = ("host", scene.hl[1])
         idx2 = S.LocationHash2D(scene.width, scene.height, scene.cell, scene.offset, capacity=cap, device=local)
         sim2 = StripSimulation(idx2, rank, world, fresh_nccl_id(dist, torch, rank), halo_capacity=halo_cap,
-                               boundaries=bounds)
+                               boundaries=bounds, peer_gather=peer_gather(dist, torch))
         sim2.add_scene_agents(scene, ids, xy, vxy)
         e2e = run_e2e(sim2, scene, min(K, 10), 3, dist, torch)
 
@@ -176,9 +177,12 @@ def run(args) -> None:
                 "workload": workload_name(workload, args.variant) + (", NoLocalPlan" if args.no_local_plan else ""),
                 "agents": n_live, "agents_per_gpu": n_live / world,
                 "strip_boundaries": "balanced by agent count (rcs_dist_set_boundaries)",
-                "parallelism": f"{world} spatial strips along x, NCCL send/recv halo (3 cell columns per side), "
-                               "ring agents advanced redundantly (no migration message); the whole step, NCCL "
-                               "exchange included, replays as one CUDA graph per rank",
+                "parallelism": f"{world} spatial strips along x, halo of 3 cell columns per side by {sim.transport} "
+                               + ("(the pack pass stores into the neighbour's memory over NVLink, a release / "
+                                  "acquire round number orders it; the whole step replays as one CUDA graph per rank)"
+                                  if sim.transport != "nccl" else
+                                  "(ncclSend / ncclRecv issued eagerly; rebuild + step kernels replay as a CUDA graph)")
+                               + ", ring agents advanced redundantly (no migration message)",
                 "mode": "frozen snapshot (RCS_STEP_NO_COMMIT)" if frozen else "committed steps",
                 "l2": "per-rank working set (two state buffer sets + index) larger than L2; no flush between steps",
                 "seed": scene.seed, "dt_ns": scene.dt[1],
@@ -189,7 +193,7 @@ def run(args) -> None:
             "e2e": e2e, "gpu_launches": int(agg[6].item()), "graph_steps_rank0": g1[0] - g0[0],
             "dist_verified": None if dist_check is None else dist_check["ok"], "dist_verify": dist_check,
             "roofline": {
-                "bound": "hbm", "kernel": "step_warp_kernel (+ step_aside_kernel) per rank, slowest rank",
+                "bound": "hbm", "kernel": "step_tile_kernel (+ step_aside_kernel) per rank, slowest rank",
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "peak_source": how, "traffic": None,
                 "algorithmic_bytes_per_agent_step": algo, "kernel_ms": k_ms,
@@ -247,7 +251,7 @@ def verify_stream(dist, torch, rank: int, world: int, local: int, K: int = 120) 
 
     cap = 4 * world * 300
     sim = StripSimulation(S.LocationHash2D(dom, dom, cell, (0.0, 0.0), capacity=cap, device=local), rank, world,
-                          fresh_nccl_id(dist, torch, rank), halo_capacity=2048)
+                          fresh_nccl_id(dist, torch, rank), halo_capacity=2048, peer_gather=peer_gather(dist, torch))
     keep = sources()
     for ss in keep:
         sim.add_source_sink(ss)
@@ -285,7 +289,7 @@ def verify_stream(dist, torch, rank: int, world: int, local: int, K: int = 120) 
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     return {"ok": bool(int(flag.item())), "n_gpus": world, "steps": K, "source_sinks": 4 * world, "live_agents": n_ref,
-            "transport": "NCCL send/recv + all-reduce of the spawn bitmap", "workload": "SourceSink stream on strips",
+            "transport": f"halo by {sim.transport}, spawn bitmap by ncclAllReduce", "workload": "SourceSink stream on strips",
             "detail": detail}
 
 
@@ -303,7 +307,8 @@ def verify_core(dist, torch, rank: int, world: int, local: int, workload: str, v
     w_cols = 1 + int(np.floor(scene.eyesight / scene.cell)) + 1  # ring + stencil reach
     halo_cap = int(1.2 * w_cols * per_col) + 2048
     idx = S.LocationHash2D(scene.width, scene.height, scene.cell, scene.offset, capacity=n_total, device=local)
-    sim = StripSimulation(idx, rank, world, nccl_id, halo_capacity=halo_cap, boundaries=scene.meta["bounds"])
+    sim = StripSimulation(idx, rank, world, nccl_id, halo_capacity=halo_cap, boundaries=scene.meta["bounds"],
+                          peer_gather=peer_gather(dist, torch))
     n0 = sim.add_scene_agents(scene, ids, xy, vxy)
     for _ in range(K):
         sim.step_async(dt)
@@ -340,7 +345,7 @@ def verify_core(dist, torch, rank: int, world: int, local: int, workload: str, v
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     return {"ok": bool(int(flag.item())), "n_gpus": world, "agents": int(n_total), "steps": K,
-            "transport": "NCCL send/recv between processes",
+            "transport": f"halo by {sim.transport}, one process per GPU",
             "workload": f"{workload}, ids {variant}, committed steps of {dt.secs + dt.nanos / 1e9:.4f} s",
             "net_migration_sum_over_ranks": int(mig[0].item()),
             "agents_with_finite_t_i_last_step": int(mig[1].item()), "detail": detail}
@@ -369,7 +374,7 @@ def run_stream(args) -> None:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lp_none = not args.c5_zanlungo
     check = None if getattr(args, "skip_verify", False) else verify_stream(dist, torch, rank, world, local)
-    sim, n_src, dom = stream_bench.build(lp_none, device=local, strip=(rank, world, fresh_nccl_id(dist, torch, rank)))
+    sim, n_src, dom = stream_bench.build(lp_none, device=local, strip=(rank, world, fresh_nccl_id(dist, torch, rank), peer_gather(dist, torch)))
     lib, h = sim._lib, sim._h
     dt = S.Duration(0, 100_000_000)
 
@@ -448,6 +453,14 @@ def verify(args) -> None:
     dist.destroy_process_group()
     if not ok:
         raise SystemExit(3)
+
+
+def peer_gather(dist, torch):
+    """The halo transport of the multi-process runs: peer stores over NVLink (default), or ncclSend / ncclRecv with
+    RCS_HALO=nccl in the environment."""
+    from .strips import torch_peer_gather
+
+    return None if os.environ.get("RCS_HALO", "peer") == "nccl" else torch_peer_gather(dist, torch)
 
 
 def fresh_nccl_id(dist, torch, rank: int) -> bytes:

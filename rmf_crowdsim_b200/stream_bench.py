@@ -18,7 +18,7 @@ import numpy as np
 
 
 def build(lp_none: bool, device: int = 0, cols: int = 32, rows: int = 256, strip=None):
-    """strip = (rank, world, nccl_id): this rank of a strip-partitioned stream.  Every rank holds all source sinks;
+    """strip = (rank, world, nccl_id[, peer_gather]): this rank of a strip-partitioned stream.  Every rank holds all source sinks;
     the rank that owns a source's cell column spawns for it (source columns are 65 c + 17 of 2112: never next to a
     boundary of 2, 4 or 8 equal strips)."""
     from . import sim as S
@@ -34,11 +34,12 @@ def build(lp_none: bool, device: int = 0, cols: int = 32, rows: int = 256, strip
     else:
         from .strips import StripSimulation
 
-        rank, world, nccl_id = strip
+        rank, world, nccl_id = strip[:3]
+        gather = strip[3] if len(strip) > 3 else None
         halo_cap = int(3 * rows * 2.5 * 1.5) + 4096  # three columns per side, ~2 agents per lane and column
         cap = int(cap / world * 1.3) + 2 * halo_cap + 8192
         idx = S.LocationHash2D(dom, dom, cell, (-margin, -margin), capacity=cap, device=device)
-        sim = StripSimulation(idx, rank, world, nccl_id, halo_capacity=halo_cap)
+        sim = StripSimulation(idx, rank, world, nccl_id, halo_capacity=halo_cap, peer_gather=gather)
     lp = S.NoLocalPlan() if lp_none else S.Zanlungo(0.05, 1.0, 0.0, 0.5, 1.0, 0.2)
     keep = [lp]
     for c in range(cols):

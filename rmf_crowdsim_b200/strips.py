@@ -62,12 +62,26 @@ def _planners(scene):
     return hl, lp
 
 
+def torch_peer_gather(dist, torch):
+    """`peer_gather` for StripSimulation over a torch.distributed process group: every rank's 64-byte CUDA IPC handle
+    to every rank (only the two neighbours' are used)."""
+    def gather(handle: bytes):
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
+        parts = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
+        dist.all_gather(parts, mine)
+        return [bytes(p.cpu().tolist()) for p in parts]
+    return gather
+
+
 class StripSimulation(S.Simulation):
-    """One rank of a strip-partitioned simulation (NCCL transport).  `nccl_id` is the 128-byte id made by
-    `nccl_unique_id()` on rank 0 and distributed by the caller (e.g. torch.distributed.broadcast)."""
+    """One rank of a strip-partitioned simulation (one process per GPU).  `nccl_id` is the 128-byte id made by
+    `nccl_unique_id()` on rank 0 and distributed by the caller (e.g. torch.distributed.broadcast).
+    `peer_gather` (e.g. `torch_peer_gather(dist, torch)`) switches the halo exchange from ncclSend / ncclRecv to the
+    peer-store transport (rcs_dist_peer_export / rcs_dist_peer_connect): every rank must pass it, and every rank must
+    have its own GPU."""
 
     def __init__(self, spatial_index: S.LocationHash2D, rank: int, world: int, nccl_id: Optional[bytes],
-                 halo_capacity: int = 0, boundaries=None):
+                 halo_capacity: int = 0, boundaries=None, peer_gather=None):
         super().__init__(spatial_index)
         self.rank, self.world = rank, world
         if boundaries is not None:  # world + 1 cell-column boundaries instead of the equal split (every rank alike)
@@ -80,6 +94,16 @@ class StripSimulation(S.Simulation):
             buf = (C.c_uint8 * 128).from_buffer_copy(nccl_id)
         N.check(self._h, self._lib.rcs_dist_init(self._h, rank, world, buf, int(halo_capacity)))
         self.c0, self.c1 = strip_columns(self, rank, world)
+        self.transport = "nccl"
+        if world > 1 and peer_gather is not None:
+            mine = (C.c_uint8 * 64)()
+            N.check(self._h, self._lib.rcs_dist_peer_export(self._h, mine))
+            handles = peer_gather(bytes(mine))
+            assert len(handles) == world and all(len(hd) == 64 for hd in handles)
+            nb = [(C.c_uint8 * 64).from_buffer_copy(handles[r]) if 0 <= r < world else None
+                  for r in (rank - 1, rank + 1)]
+            N.check(self._h, self._lib.rcs_dist_peer_connect(self._h, nb[0], nb[1]))
+            self.transport = "peer stores"
 
     def add_scene_agents(self, scene, ids: Optional[np.ndarray] = None, xy=None, vxy=None) -> int:
         """Adds the agents of `scene` (or of the given id / xy / vxy arrays) that fall into this strip."""
