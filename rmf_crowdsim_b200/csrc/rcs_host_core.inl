@@ -87,10 +87,18 @@ static int exclusive_scan(rcs_sim* s, const uint32_t* in, uint64_t len, uint32_t
     CU_TRY(s, dalloc(&s->tile_sums, tiles + 1024));
     s->tile_sums_cap = tiles + 1024;
   }
-  scan_reduce_kernel<<<(uint32_t)tiles, SCAN_THREADS, 0, s->stream>>>(in, len, s->tile_sums);
-  scan_tile_sums_kernel<<<1, SCAN_THREADS, 0, s->stream>>>(s->tile_sums, (uint32_t)tiles, s->scan_total);
-  scan_apply_kernel<<<(uint32_t)tiles, SCAN_THREADS, 0, s->stream>>>(in, len, s->tile_sums, out, cursor);
-  s->launches += 3;
+  if (tiles <= 8192) {
+    // the cell histogram of a step (4096 tiles at 2^24 cells): every block of the apply pass sums the tiles before
+    // its own, a single tile needs no sums at all
+    if (tiles > 1) scan_reduce_kernel<<<(uint32_t)tiles, SCAN_THREADS, 0, s->stream>>>(in, len, s->tile_sums);
+    scan_apply_kernel<true><<<(uint32_t)tiles, SCAN_THREADS, 0, s->stream>>>(in, len, s->tile_sums, out, cursor);
+    s->launches += tiles > 1 ? 2 : 1;
+  } else {
+    scan_reduce_kernel<<<(uint32_t)tiles, SCAN_THREADS, 0, s->stream>>>(in, len, s->tile_sums);
+    scan_tile_sums_kernel<<<1, SCAN_THREADS, 0, s->stream>>>(s->tile_sums, (uint32_t)tiles, s->scan_total);
+    scan_apply_kernel<false><<<(uint32_t)tiles, SCAN_THREADS, 0, s->stream>>>(in, len, s->tile_sums, out, cursor);
+    s->launches += 3;
+  }
   CU_TRY(s, cudaGetLastError());
   return RCS_OK;
 }

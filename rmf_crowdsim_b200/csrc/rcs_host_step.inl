@@ -290,9 +290,8 @@ static int step_phase_b(rcs_sim* s, double dt, uint32_t flags) {
       const uint32_t ghosts_ub = rl.cap + rr.cap;
       halo_unpack_kernel<<<blocks_for(ghosts_ub, 256), 256, 0, s->stream>>>(
           s->cur, s->keep, (uint32_t)s->cap, rl, rr, has_l, has_r, s->cnt, s->d_status,
-          s->peer.enabled ? s->peer.xseq : nullptr);
-      s->launches += 1;
-      rc = bin_agents(s, n_ub, s->cnt + CNT_CUR, ghosts_ub);
+          s->peer.enabled ? s->peer.xseq : nullptr, s->grid, s->cellid, s->cell_count, s->cell_lo, s->cell_hi);
+      s->launches += 1;  // (the ghosts are binned on the way: no second pass over them)
     } else if (!s->binned_ahead) {
       rc = clear_histogram(s);
       if (rc) return rc;

@@ -144,6 +144,31 @@ constexpr uint32_t CELL_DEAD = 0xffffffffu;
 // ---------------------------------------------------------------------------------------------
 // A1/A2: cell of every agent (LocationHash2D::location_to_index) + histogram.
 // ---------------------------------------------------------------------------------------------
+// Files agent i (position p) under its insert cell: cellid[i] and the histogram.  False: not indexed (cellid = dead).
+__device__ __forceinline__ bool bin_one(const GridDev& g, uint32_t i, double2 p, uint32_t* __restrict__ cellid,
+                                        uint32_t* __restrict__ cell_count, uint64_t cell_lo, uint64_t cell_hi,
+                                        DevStatus* status, uint64_t& idx) {
+  if (!location_to_index(g, p.x, p.y, idx)) {
+    // only reachable through snapshot injection; steps never commit an out-of-bounds position
+    cellid[i] = CELL_DEAD;
+    atomicAdd(&status->oob_count, 1u);
+    return false;
+  }
+  if (idx < cell_lo || idx >= cell_hi) {
+    // strips index only the cells of their own columns and halo; an agent elsewhere (possible only through the
+    // row aliasing of location_hash_2d.rs:59 far above the grid) cannot be handled by this rank
+    cellid[i] = CELL_DEAD;
+    atomicAdd(&status->halo_err, 1u);
+    return false;
+  }
+  cellid[i] = (uint32_t)idx;
+  // The agents arrive in last step's canonical order, so the lanes of a warp fall into a handful of cells: one
+  // atomic per distinct cell of the warp instead of one per agent.
+  const unsigned peers = __match_any_sync(__activemask(), (uint32_t)idx);
+  if ((threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&cell_count[idx], (unsigned)__popc(peers));
+  return true;
+}
+
 // Agents [*first (0 if null), min(n_ub, *last)) of the unsorted arrays.  Entries whose keep flag is 0 (despawned
 // at a sink, migrated to another strip, ghosts of the previous step) are dropped here: the counting sort of the
 // next step is the stream compaction.
@@ -159,29 +184,10 @@ __global__ void bin_count_kernel(GridDev g, uint32_t n_ub, const uint32_t* __res
     cellid[i] = CELL_DEAD;
     return;
   }
-  uint64_t idx;
   const double2 p = pos[i];
-  if (location_to_index(g, p.x, p.y, idx)) {
-    if (idx < cell_lo || idx >= cell_hi) {
-      // strips index only the cells of their own columns and halo; an agent elsewhere (possible only through the
-      // row aliasing of location_hash_2d.rs:59 far above the grid) cannot be handled by this rank
-      cellid[i] = CELL_DEAD;
-      atomicAdd(&status->halo_err, 1u);
-      return;
-    }
-    cellid[i] = (uint32_t)idx;
-    {
-      // The agents arrive in last step's canonical order, so the lanes of a warp fall into a handful of cells: one
-      // atomic per distinct cell of the warp instead of one per agent.
-      const unsigned peers = __match_any_sync(__activemask(), (uint32_t)idx);
-      if ((threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&cell_count[idx], (unsigned)__popc(peers));
-    }
-    if (pk.enabled) halo_pack_one(pk, i, (uint32_t)idx, status);
-  } else {
-    // only reachable through snapshot injection; steps never commit an out-of-bounds position
-    cellid[i] = CELL_DEAD;
-    atomicAdd(&status->oob_count, 1u);
-  }
+  uint64_t idx;
+  if (bin_one(g, i, p, cellid, cell_count, cell_lo, cell_hi, status, idx) && pk.enabled)
+    halo_pack_one(pk, i, (uint32_t)idx, status);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -255,6 +261,9 @@ __global__ void scan_tile_sums_kernel(uint32_t* __restrict__ tile_sums, uint32_t
 
 // writes cell_start[c] (exclusive) and cursor[c] (= cell_start[c], bumped by the scatter); the
 // thread that owns the last element also writes cell_start[len] = total.
+// RAW_SUMS: tile_sums holds the tiles' totals as scan_reduce_kernel left them and every block adds up the ones before
+// its own (a few thousand tiles at most: one launch less than scanning them first).
+template <bool RAW_SUMS>
 __global__ void scan_apply_kernel(const uint32_t* __restrict__ in, uint64_t len,
                                   const uint32_t* __restrict__ tile_sums, uint32_t* __restrict__ cell_start,
                                   uint32_t* __restrict__ cursor) {
@@ -277,8 +286,15 @@ __global__ void scan_apply_kernel(const uint32_t* __restrict__ in, uint64_t len,
   }
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; ++k) s += v[k];
-  uint32_t total;
-  uint32_t run = tile_sums[blockIdx.x] + block_exclusive_scan(s, total);
+  uint32_t total, before;
+  if (RAW_SUMS) {
+    uint32_t part = 0;
+    for (uint32_t t = threadIdx.x; t < blockIdx.x; t += SCAN_THREADS) part += tile_sums[t];
+    (void)block_exclusive_scan(part, before);
+  } else {
+    before = tile_sums[blockIdx.x];
+  }
+  uint32_t run = before + block_exclusive_scan(s, total);
   if (base + SCAN_ITEMS <= len) {
     uint32_t o[SCAN_ITEMS];
 #pragma unroll
@@ -1554,7 +1570,8 @@ constexpr unsigned long long HALO_WAIT_NS = 30ull * 1000000000ull;
 
 __global__ void halo_unpack_kernel(AgentArrays cur, uint32_t* __restrict__ keep, uint32_t cap, HaloBuf left,
                                    HaloBuf right, int has_left, int has_right, uint32_t* cnt, DevStatus* status,
-                                   const uint32_t* __restrict__ xseq) {
+                                   const uint32_t* __restrict__ xseq, GridDev g, uint32_t* __restrict__ cellid,
+                                   uint32_t* __restrict__ cell_count, uint64_t cell_lo, uint64_t cell_hi) {
   uint32_t par = 0u;
   if (xseq) {
     // wait for both neighbours' rounds (another GPU's kernel releases them; bounded, so a dead peer fails the step
@@ -1610,7 +1627,8 @@ __global__ void halo_unpack_kernel(AgentArrays cur, uint32_t* __restrict__ keep,
   const uint32_t slot = n0 + k;
   if (slot >= cap) return;
   // (L1 is not coherent with another GPU's stores: the rows are read at L2)
-  cur.pos[slot] = __ldcg(b.pos + e);
+  const double2 p = __ldcg(b.pos + e);
+  cur.pos[slot] = p;
   cur.vel[slot] = __ldcg(b.vel + e);
   cur.id[slot] = __ldcg(b.id + e);
   const unsigned long long meta = __ldcg(b.meta + e);
@@ -1618,6 +1636,8 @@ __global__ void halo_unpack_kernel(AgentArrays cur, uint32_t* __restrict__ keep,
   cur.wp[slot] = (uint32_t)(meta >> 32);
   keep[slot] = 1u;
   if (cur.pv) cur.pv[slot] = __ldcg(b.pv + e);
+  uint64_t idx;
+  (void)bin_one(g, slot, p, cellid, cell_count, cell_lo, cell_hi, status, idx);  // ghosts join the owned histogram
 }
 
 // FP64 pipe peak: independent DFMA / DADD chains.
