@@ -66,11 +66,18 @@ def torch_peer_gather(dist, torch):
     """`peer_gather` for StripSimulation over a torch.distributed process group: every rank's 64-byte CUDA IPC handle
     to every rank (only the two neighbours' are used)."""
     def gather(handle: bytes):
-        mine = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
         parts = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
         dist.all_gather(parts, mine)
         return [bytes(p.cpu().tolist()) for p in parts]
     return gather
+
+
+def neighbour_handles(handles, rank: int, world: int):
+    """(left, right) of `rank` out of the all-gathered handles; None where the strip has no neighbour."""
+    assert len(handles) == world and all(len(hd) == 64 for hd in handles)
+    return tuple(handles[r] if 0 <= r < world else None for r in (rank - 1, rank + 1))
 
 
 class StripSimulation(S.Simulation):
@@ -98,10 +105,8 @@ class StripSimulation(S.Simulation):
         if world > 1 and peer_gather is not None:
             mine = (C.c_uint8 * 64)()
             N.check(self._h, self._lib.rcs_dist_peer_export(self._h, mine))
-            handles = peer_gather(bytes(mine))
-            assert len(handles) == world and all(len(hd) == 64 for hd in handles)
-            nb = [(C.c_uint8 * 64).from_buffer_copy(handles[r]) if 0 <= r < world else None
-                  for r in (rank - 1, rank + 1)]
+            nb = [None if hd is None else (C.c_uint8 * 64).from_buffer_copy(hd)
+                  for hd in neighbour_handles(peer_gather(bytes(mine)), rank, world)]
             N.check(self._h, self._lib.rcs_dist_peer_connect(self._h, nb[0], nb[1]))
             self.transport = "peer stores"
 

@@ -1,5 +1,5 @@
 """CPU, world_size 2 and 3 over gloo: the host-side logic of the multi-GPU path (rank-local crowd generation,
-strip ownership, the exchange of the 128-byte communicator id, max-over-ranks timing reduction).  No CUDA."""
+strip ownership, the exchange of the 128-byte communicator id and of the peer-store handles, max-over-ranks timing reduction).  No CUDA."""
 import os
 import socket
 
@@ -11,7 +11,7 @@ import torch.multiprocessing as mp
 
 from rmf_crowdsim_b200 import dist_bench as DB
 from rmf_crowdsim_b200 import scenes as SC
-from rmf_crowdsim_b200.strips import column_of, owned_mask
+from rmf_crowdsim_b200.strips import column_of, neighbour_handles, owned_mask, torch_peer_gather
 
 
 def _free_port() -> int:
@@ -49,6 +49,11 @@ def _worker(rank: int, world: int, port: int, variant: str, q):
             ident = torch.arange(128, dtype=torch.uint8)
         dist.broadcast(ident, 0)
         assert bytes(ident.tolist()) == bytes(range(128))
+        # the peer-store transport's handle exchange: every rank's 64-byte IPC handle to every rank, neighbours picked
+        mine = bytes([rank + 1] * 64)
+        left, right = neighbour_handles(torch_peer_gather(dist, torch)(mine), rank, world)
+        assert left == (bytes([rank] * 64) if rank > 0 else None)
+        assert right == (bytes([rank + 2] * 64) if rank + 1 < world else None)
         # device-time reduction used for `value`: max over ranks
         ms = torch.tensor([10.0 + rank], dtype=torch.float64)
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
