@@ -225,7 +225,7 @@ static int bin_agents(rcs_sim* s, uint32_t n_ub, const uint32_t* first, uint32_t
     CU_TRY(s, cudaGetLastError());
     return RCS_OK;
   }
-  bin_count_kernel<<<blocks_for(launch_n, 256), 256, 0, s->stream>>>(s->grid, n_ub, first, s->cnt + CNT_TOT, s->cur.pos,
+  bin_count_kernel<<<blocks_for(launch_n, BIN_THREADS), BIN_THREADS, 0, s->stream>>>(s->grid, n_ub, first, s->cnt + CNT_TOT, s->cur.pos,
                                                                  s->cur_has_dead ? s->keep : nullptr,
                                                                  s->cellid, s->cell_count, s->cell_lo, s->cell_hi,
                                                                  pk, s->d_status);

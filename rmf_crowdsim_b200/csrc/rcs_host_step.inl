@@ -238,11 +238,6 @@ static int step_phase_a2(rcs_sim* s, double dt) {
     }
     if (rc) return rc;
     if (s->ev_packed) CU_TRY(s, cudaEventRecord(s->ev_packed, s->stream));
-    if (s->peer.enabled) {  // the exchange: count, failed flag and the round number, behind the rows of the pack pass
-      halo_publish_kernel<<<1, 32, 0, s->stream>>>(s->peer.xseq, s->send_l.buf.count, s->send_r.buf.count,
-                                                   s->peer.remote_hdr[0], s->peer.remote_hdr[1]);
-      s->launches += 1;
-    }
   }
   CU_TRY(s, cudaGetLastError());
   return RCS_OK;
@@ -290,7 +285,8 @@ static int step_phase_b(rcs_sim* s, double dt, uint32_t flags) {
       const uint32_t ghosts_ub = rl.cap + rr.cap;
       halo_unpack_kernel<<<blocks_for(ghosts_ub, 256), 256, 0, s->stream>>>(
           s->cur, s->keep, (uint32_t)s->cap, rl, rr, has_l, has_r, s->cnt, s->d_status,
-          s->peer.enabled ? s->peer.xseq : nullptr, s->grid, s->cellid, s->cell_count, s->cell_lo, s->cell_hi);
+          s->peer.enabled ? s->peer.xseq : nullptr, s->grid, s->cellid, s->cell_count, s->cell_lo, s->cell_hi,
+          s->send_l.buf.count, s->send_r.buf.count, s->peer.remote_hdr[0], s->peer.remote_hdr[1]);
       s->launches += 1;  // (the ghosts are binned on the way: no second pass over them)
     } else if (!s->binned_ahead) {
       rc = clear_histogram(s);

@@ -124,6 +124,52 @@ __device__ __forceinline__ void halo_pack_one(const PackArgs& pk, uint32_t i, ui
   }
 }
 
+// The same for a whole block of the binning pass (every thread of the block calls it, `mine` = this thread has an agent
+// to test): ONE append per block and side.  The boundary columns are contiguous in storage, so ~100 blocks per side
+// pack; with one atomic per warp the 770 same-address atomics per side were most of the pass's extra time on 8 strips.
+template <int THREADS>
+__device__ __forceinline__ void halo_pack_block(const PackArgs& pk, bool mine, uint32_t i, uint32_t idx,
+                                                DevStatus* status) {
+  constexpr int NW = THREADS / 32;
+  __shared__ uint32_t s_cnt[2][NW];
+  __shared__ uint32_t s_base[2];
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t par = pk.xseq ? (*pk.xseq & 1u) : 0u;
+  const uint32_t cx = idx / pk.nx;
+  const bool send0 = mine && pk.has_left && cx < pk.st.c0 + pk.width;
+  const bool send1 = mine && pk.has_right && cx + pk.width >= pk.st.c1;
+  const unsigned m0 = __ballot_sync(0xffffffffu, send0), m1 = __ballot_sync(0xffffffffu, send1);
+  if (lane == 0) {
+    s_cnt[0][warp] = __popc(m0);
+    s_cnt[1][warp] = __popc(m1);
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    uint32_t tot = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) tot += s_cnt[threadIdx.x][w];
+    s_base[threadIdx.x] = tot ? atomicAdd(threadIdx.x == 0 ? pk.left.count : pk.right.count, tot) : 0u;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    if (!(side == 0 ? send0 : send1)) continue;
+    const HaloBuf& b = side == 0 ? pk.left : pk.right;
+    uint32_t k = s_base[side] + __popc((side == 0 ? m0 : m1) & ((1u << lane) - 1u));
+    for (unsigned w = 0; w < warp; ++w) k += s_cnt[side][w];
+    if (k >= b.cap) {
+      atomicAdd(&status->capacity_err, 1u);
+      continue;
+    }
+    k += par * b.cap;  // peer-store transport: the rows go straight into the neighbour's receive buffer
+    b.pos[k] = pk.cur.pos[i];
+    b.vel[k] = pk.cur.vel[i];
+    b.id[k] = pk.cur.id[i];
+    b.meta[k] = (unsigned long long)pk.cur.grp[i] | ((unsigned long long)pk.cur.wp[i] << 32);
+    if (pk.cur.pv) b.pv[k] = pk.cur.pv[i];
+  }
+}
+
 // Strips, when the previous step's epilogue has already binned the owned agents (cellid, histogram): only the halo
 // pack of the binning pass is left to do.
 __global__ void halo_pack_kernel(uint32_t n_ub, const uint32_t* __restrict__ last, const uint32_t* __restrict__ cellid,
@@ -140,6 +186,7 @@ constexpr int SCAN_ITEMS = 16;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 constexpr int SORT_LOCAL_MAX = 32;
 constexpr uint32_t CELL_DEAD = 0xffffffffu;
+constexpr int BIN_THREADS = 256;  // block size of bin_count_kernel
 
 // ---------------------------------------------------------------------------------------------
 // A1/A2: cell of every agent (LocationHash2D::location_to_index) + histogram.
@@ -172,22 +219,21 @@ __device__ __forceinline__ bool bin_one(const GridDev& g, uint32_t i, double2 p,
 // Agents [*first (0 if null), min(n_ub, *last)) of the unsorted arrays.  Entries whose keep flag is 0 (despawned
 // at a sink, migrated to another strip, ghosts of the previous step) are dropped here: the counting sort of the
 // next step is the stream compaction.
-__global__ void bin_count_kernel(GridDev g, uint32_t n_ub, const uint32_t* __restrict__ first,
+__global__ void __launch_bounds__(BIN_THREADS) bin_count_kernel(GridDev g, uint32_t n_ub, const uint32_t* __restrict__ first,
                                  const uint32_t* __restrict__ last, const double2* __restrict__ pos,
                                  const uint32_t* __restrict__ keep,
                                  uint32_t* __restrict__ cellid, uint32_t* __restrict__ cell_count, uint64_t cell_lo,
                                  uint64_t cell_hi, PackArgs pk, DevStatus* status) {
   if (status->failed) return;
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x + (first ? *first : 0u);
-  if (i >= n_ub || i >= *last) return;
-  if (keep && !keep[i]) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x + (first ? *first : 0u);
+  bool live = i < n_ub && i < *last;
+  if (live && keep && !keep[i]) {
     cellid[i] = CELL_DEAD;
-    return;
+    live = false;
   }
-  const double2 p = pos[i];
-  uint64_t idx;
-  if (bin_one(g, i, p, cellid, cell_count, cell_lo, cell_hi, status, idx) && pk.enabled)
-    halo_pack_one(pk, i, (uint32_t)idx, status);
+  uint64_t idx = 0;
+  if (live) live = bin_one(g, i, pos[i], cellid, cell_count, cell_lo, cell_hi, status, idx);
+  if (pk.enabled) halo_pack_block<BIN_THREADS>(pk, live, i, (uint32_t)idx, status);  // (the whole block gets here)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1549,17 +1595,13 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   return t;
 }
 
-// header of one half of a receive buffer: [count, failed, round, pad]
-__global__ void halo_publish_kernel(const uint32_t* __restrict__ xseq, const uint32_t* __restrict__ send_l_hdr,
-                                    const uint32_t* __restrict__ send_r_hdr, uint32_t* remote_l_hdr,
-                                    uint32_t* remote_r_hdr) {
-  const uint32_t seq = *xseq, par = seq & 1u;
-  const uint32_t* src = threadIdx.x == 0 ? send_l_hdr : send_r_hdr;
-  uint32_t* dst = threadIdx.x == 0 ? remote_l_hdr : remote_r_hdr;
-  if (threadIdx.x > 1 || !dst) return;
-  dst += 4u * par;
-  dst[0] = src[0];
-  dst[1] = src[1];
+// header of one half of a receive buffer: [count, failed, round, pad].  Run by threads 0 and 1 of the first block of
+// halo_unpack_kernel, i.e. after the pack pass has completed (stream order) and before anybody waits.
+__device__ __forceinline__ void halo_publish(uint32_t seq, const uint32_t* __restrict__ send_hdr, uint32_t* remote_hdr) {
+  if (!remote_hdr) return;
+  uint32_t* dst = remote_hdr + 4u * (seq & 1u);
+  dst[0] = send_hdr[0];
+  dst[1] = send_hdr[1];
   // the rows were stored by the kernel before this one; the fence orders them (and the two words above) before the
   // round number for an observer on the other GPU
   __threadfence_system();
@@ -1571,9 +1613,13 @@ constexpr unsigned long long HALO_WAIT_NS = 30ull * 1000000000ull;
 __global__ void halo_unpack_kernel(AgentArrays cur, uint32_t* __restrict__ keep, uint32_t cap, HaloBuf left,
                                    HaloBuf right, int has_left, int has_right, uint32_t* cnt, DevStatus* status,
                                    const uint32_t* __restrict__ xseq, GridDev g, uint32_t* __restrict__ cellid,
-                                   uint32_t* __restrict__ cell_count, uint64_t cell_lo, uint64_t cell_hi) {
+                                   uint32_t* __restrict__ cell_count, uint64_t cell_lo, uint64_t cell_hi,
+                                   const uint32_t* __restrict__ send_l_hdr, const uint32_t* __restrict__ send_r_hdr,
+                                   uint32_t* remote_l_hdr, uint32_t* remote_r_hdr) {
   uint32_t par = 0u;
   if (xseq) {
+    if (blockIdx.x == 0 && threadIdx.x < 2)  // this rank's own round first: nobody waits for a rank that waits
+      halo_publish(*xseq, threadIdx.x == 0 ? send_l_hdr : send_r_hdr, threadIdx.x == 0 ? remote_l_hdr : remote_r_hdr);
     // wait for both neighbours' rounds (another GPU's kernel releases them; bounded, so a dead peer fails the step
     // instead of hanging the device)
     __shared__ uint32_t s_ok;
