@@ -306,11 +306,16 @@ static void launch_step_kernel(rcs_sim* s, const StepArgs& a, uint32_t n_ub, boo
   if (sorted_input && (s->opt_step_kernel == 0 || s->opt_step_kernel == 3)) {
     // stencil staged in shared memory (rcs_step_tile.cuh); agents it cannot stage go to step_aside_kernel's lists
     if (!s->tile_attr_set) {  // per device context
-      cudaFuncSetAttribute(step_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared));
-      cudaFuncSetAttribute(step_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      cudaFuncSetAttribute(step_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared));
+      cudaFuncSetAttribute(step_tile_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      cudaFuncSetAttribute(step_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared));
+      cudaFuncSetAttribute(step_tile_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
       s->tile_attr_set = true;
     }
-    step_tile_kernel<<<blocks_for(n_ub, 32 * ST_WARPS), 32 * ST_WARPS, sizeof(TileShared), s->stream>>>(a);
+    if (a.strip.enabled)
+      step_tile_kernel<true><<<blocks_for(n_ub, 32 * ST_WARPS), 32 * ST_WARPS, sizeof(TileShared), s->stream>>>(a);
+    else
+      step_tile_kernel<false><<<blocks_for(n_ub, 32 * ST_WARPS), 32 * ST_WARPS, sizeof(TileShared), s->stream>>>(a);
     step_aside_kernel<<<148 * 4, 32 * SW_WARPS, 0, s->stream>>>(a);
     s->launches += 2;
   } else if (sorted_input && s->opt_step_kernel != 1) {

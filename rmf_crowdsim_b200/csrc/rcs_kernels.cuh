@@ -673,16 +673,31 @@ struct StepArgs {
 constexpr uint32_t WP_MASK = 0xffffu;
 constexpr int WP_ROUTE_SHIFT = 16;
 
-enum : uint32_t { ROLE_PASSIVE = 0, ROLE_OWN = 1, ROLE_RING = 2 };
+enum : uint32_t { ROLE_PASSIVE = 0, ROLE_OWN = 1, ROLE_RING = 2, ROLE_MASK = 3,
+                  // optional, for integrate_and_store: the old column lies within h of the left / right boundary
+                  ROLE_NEAR_L = 1u << 8, ROLE_NEAR_R = 1u << 9, ROLE_HAS_NEAR = 1u << 10 };
 
 // Strips: an agent is advanced by the rank that owns its column AND, redundantly and bit-identically,
 // by the neighbour rank that holds it in the inner halo ring (so migration needs no message).
-__device__ __forceinline__ uint32_t agent_role(const StepArgs& a, uint32_t i) {
+__device__ __forceinline__ uint32_t agent_role_of_cell(const StepArgs& a, uint32_t cell) {
   if (!a.strip.enabled) return ROLE_OWN;
-  const uint32_t cx = a.cell[i] / (uint32_t)a.grid.nx;
+  const uint32_t cx = cell / (uint32_t)a.grid.nx;
   if (cx >= a.strip.c0 && cx < a.strip.c1) return ROLE_OWN;
   if (cx + a.strip.h >= a.strip.c0 && cx < a.strip.c1 + a.strip.h) return ROLE_RING;
   return ROLE_PASSIVE;
+}
+// ... with the boundary bits, so that the epilogue needs neither the cell nor a second division
+__device__ __forceinline__ uint32_t agent_role_and_bits(const StepArgs& a, uint32_t cell) {
+  const uint32_t cx = cell / (uint32_t)a.grid.nx;
+  uint32_t r = ROLE_PASSIVE;
+  if (cx >= a.strip.c0 && cx < a.strip.c1) r = ROLE_OWN;
+  else if (cx + a.strip.h >= a.strip.c0 && cx < a.strip.c1 + a.strip.h) r = ROLE_RING;
+  if (cx < a.strip.c0 + a.strip.h) r |= ROLE_NEAR_L;
+  if (cx + a.strip.h >= a.strip.c1) r |= ROLE_NEAR_R;
+  return r | ROLE_HAS_NEAR;
+}
+__device__ __forceinline__ uint32_t agent_role(const StepArgs& a, uint32_t i) {
+  return a.strip.enabled ? agent_role_of_cell(a, a.cell[i]) : (uint32_t)ROLE_OWN;
 }
 
 // An entry of the sorted arrays that this rank does not advance (ghost beyond the ring, slot beyond the live count):
@@ -832,6 +847,8 @@ __device__ __forceinline__ void high_level_velocity(const StepArgs& a, uint32_t 
 
 // Explicit Euler + commit outputs + error accounting (lib.rs:295-302), then the waypoint / sink test on
 // the OLD position (lib.rs:305-336) and, for strips, the ownership decision by the NEW position.
+// MAY_STRIP = false: the caller knows the handle is no strip (the strip bookkeeping is compiled out).
+template <bool MAY_STRIP = true>
 __device__ __forceinline__ void integrate_and_store(const StepArgs& a, uint32_t i, const Self& me, const GroupDev& g,
                                                     uint32_t grp, uint32_t wp_in, uint32_t role, double velx,
                                                     double vely, double t_i, double fx, double fy, uint32_t nbc) {
@@ -839,7 +856,7 @@ __device__ __forceinline__ void integrate_and_store(const StepArgs& a, uint32_t 
   const double ny = me.py + vely * a.dt;
   a.opos[i] = make_double2(nx, ny);
   a.ovel[i] = make_double2(velx, vely);
-  const bool own = role == ROLE_OWN;
+  const bool own = (role & ROLE_MASK) == ROLE_OWN;
   if (a.t_i) {
     a.t_i[i] = t_i;
     a.fx[i] = fx;
@@ -898,15 +915,19 @@ __device__ __forceinline__ void integrate_and_store(const StepArgs& a, uint32_t 
   a.ogrp[i] = grp;
   a.owp[i] = wp | (rwp << WP_ROUTE_SHIFT);
   if (a.opv) a.opv[i] = a.in.pv[i];
-  if (a.strip.enabled) {
+  if (MAY_STRIP && a.strip.enabled) {
     // The agent stays with the rank that owns its NEW column.  Every agent that leaves a strip must have
     // been in the neighbour's ring (old column within h of the boundary) and must land inside the
     // neighbour's strip; otherwise no rank would keep it.
-    const uint32_t ocx = a.cell[i] / (uint32_t)a.grid.nx;
     const bool mine = inb && x_idx >= a.strip.c0 && x_idx < a.strip.c1;
     if (own && inb && !mine) {
-      const bool ok = x_idx < a.strip.c0 ? (ocx < a.strip.c0 + a.strip.h && x_idx >= a.strip.lc0)
-                                         : (ocx + a.strip.h >= a.strip.c1 && x_idx < a.strip.rc1);
+      bool near_l = (role & ROLE_NEAR_L) != 0u, near_r = (role & ROLE_NEAR_R) != 0u;
+      if (!(role & ROLE_HAS_NEAR)) {
+        const uint32_t ocx = a.cell[i] / (uint32_t)a.grid.nx;
+        near_l = ocx < a.strip.c0 + a.strip.h;
+        near_r = ocx + a.strip.h >= a.strip.c1;
+      }
+      const bool ok = x_idx < a.strip.c0 ? (near_l && x_idx >= a.strip.lc0) : (near_r && x_idx < a.strip.rc1);
       if (!ok) atomicAdd(&a.status->halo_err, 1u);
     }
     // a query from the top `reach` rows of the grid runs over into the NEXT column's bottom cells (y_idx >= n_x

@@ -171,6 +171,8 @@ __device__ __noinline__ void st_flush_hits(TileWarp& w, uint32_t n_hit, const do
   __syncwarp();
 }
 
+// STRIPS: the handle is a strip (ownership roles, keep flags by the new column); the plain form has none of that code.
+template <bool STRIPS>
 __global__ void __launch_bounds__(32 * ST_WARPS, RCS_TILE_BLOCKS) step_tile_kernel(StepArgs a) {
   extern __shared__ __align__(16) unsigned char st_smem_raw[];
   TileShared& sh = *reinterpret_cast<TileShared*>(st_smem_raw);
@@ -185,10 +187,13 @@ __global__ void __launch_bounds__(32 * ST_WARPS, RCS_TILE_BLOCKS) step_tile_kern
   me.px = me.py = me.vx = me.vy = me.pfx = me.pfy = 0.0;
   me.id = 0;
   me.rwp = 0u;
-  uint32_t grp = 0, wp_in = 0;
+  uint32_t grp = 0, wp_in = 0, cell_i = 0;
   uint4 sl = make_uint4(0u, 0u, 0u, 0u);
   const bool inb = i < a.n;
   if (inb) {
+    // (strips: the agent's cell decides its role; loaded here, with the own row, it is not one more global-memory
+    // latency in front of everything behind the barrier -- that was 4 % of the kernel on a strip handle)
+    if (STRIPS) cell_i = a.cell[i];
     const double2 p0 = a.in.pos[i], v0 = a.in.vel[i];
     me.px = p0.x;
     me.py = p0.y;
@@ -226,9 +231,10 @@ __global__ void __launch_bounds__(32 * ST_WARPS, RCS_TILE_BLOCKS) step_tile_kern
       }
     }
   }
+  const uint32_t role_i = STRIPS ? agent_role_and_bits(a, cell_i) : (uint32_t)ROLE_OWN;
+  const uint32_t n_live = *a.n_sorted;
   __syncthreads();  // the barrier is initialised (and nobody leaves before the copies were issued)
   if (failed) return;
-  const uint32_t n_live = *a.n_sorted;
   bool active = inb && (i < n_live);
 
   double velx = 0.0, vely = 0.0, thr2 = 0.0, rr = 0.0;
@@ -238,8 +244,8 @@ __global__ void __launch_bounds__(32 * ST_WARPS, RCS_TILE_BLOCKS) step_tile_kern
   double t_i = RCS_INF, fx = 0.0, fy = 0.0;
 
   if (active) {
-    role = agent_role(a, i);
-    if (role == ROLE_PASSIVE) {
+    role = role_i;
+    if ((role & ROLE_MASK) == ROLE_PASSIVE) {
       active = false;
       drop_entry(a, i);
     }
@@ -561,10 +567,10 @@ __global__ void __launch_bounds__(32 * ST_WARPS, RCS_TILE_BLOCKS) step_tile_kern
       velx = velx + fx * g.inv_mass;
       vely = vely + fy * g.inv_mass;
     }
-    integrate_and_store(a, i, me, g, grp, wp_in, role, velx, vely, t_i, fx, fy, nbc);
+    integrate_and_store<STRIPS>(a, i, me, g, grp, wp_in, role, velx, vely, t_i, fx, fy, nbc);
   }
   if (a.collect_stats) {  // per owned agent, so that the totals add up over ranks; one set of atomics per block
-    const bool own = active && role == ROLE_OWN;
+    const bool own = active && (role & ROLE_MASK) == ROLE_OWN;
     const uint32_t c = __reduce_add_sync(FULL, own ? cand : 0u);
     const uint32_t nb = __reduce_add_sync(FULL, own ? nbc : 0u);
     const uint32_t ft = __reduce_add_sync(FULL, (own && zan && t_i != RCS_INF) ? 1u : 0u);
