@@ -225,10 +225,15 @@ static int bin_agents(rcs_sim* s, uint32_t n_ub, const uint32_t* first, uint32_t
     CU_TRY(s, cudaGetLastError());
     return RCS_OK;
   }
-  bin_count_kernel<<<blocks_for(launch_n, BIN_THREADS), BIN_THREADS, 0, s->stream>>>(s->grid, n_ub, first, s->cnt + CNT_TOT, s->cur.pos,
-                                                                 s->cur_has_dead ? s->keep : nullptr,
-                                                                 s->cellid, s->cell_count, s->cell_lo, s->cell_hi,
-                                                                 pk, s->d_status);
+  const uint32_t* dead = s->cur_has_dead ? s->keep : nullptr;
+  if (pack)
+    bin_count_kernel<true><<<blocks_for(launch_n, BIN_THREADS), BIN_THREADS, 0, s->stream>>>(
+        s->grid, n_ub, first, s->cnt + CNT_TOT, s->cur.pos, dead, s->cellid, s->cell_count, s->cell_lo, s->cell_hi, pk,
+        s->d_status);
+  else
+    bin_count_kernel<false><<<blocks_for(launch_n, BIN_THREADS), BIN_THREADS, 0, s->stream>>>(
+        s->grid, n_ub, first, s->cnt + CNT_TOT, s->cur.pos, dead, s->cellid, s->cell_count, s->cell_lo, s->cell_hi, pk,
+        s->d_status);
   s->launches += 1;
   CU_TRY(s, cudaGetLastError());
   return RCS_OK;

@@ -219,21 +219,25 @@ __device__ __forceinline__ bool bin_one(const GridDev& g, uint32_t i, double2 p,
 // Agents [*first (0 if null), min(n_ub, *last)) of the unsorted arrays.  Entries whose keep flag is 0 (despawned
 // at a sink, migrated to another strip, ghosts of the previous step) are dropped here: the counting sort of the
 // next step is the stream compaction.
-__global__ void __launch_bounds__(BIN_THREADS) bin_count_kernel(GridDev g, uint32_t n_ub, const uint32_t* __restrict__ first,
-                                 const uint32_t* __restrict__ last, const double2* __restrict__ pos,
-                                 const uint32_t* __restrict__ keep,
-                                 uint32_t* __restrict__ cellid, uint32_t* __restrict__ cell_count, uint64_t cell_lo,
-                                 uint64_t cell_hi, PackArgs pk, DevStatus* status) {
+// PACK: the strip form (every thread of a block reaches the block-wide halo append); the plain form leaves early and
+// keeps the registers for 2048 resident threads (the pass is latency-bound on its loads and atomics).
+template <bool PACK>
+__global__ void __launch_bounds__(BIN_THREADS, 8) bin_count_kernel(
+    GridDev g, uint32_t n_ub, const uint32_t* __restrict__ first, const uint32_t* __restrict__ last,
+    const double2* __restrict__ pos, const uint32_t* __restrict__ keep, uint32_t* __restrict__ cellid,
+    uint32_t* __restrict__ cell_count, uint64_t cell_lo, uint64_t cell_hi, PackArgs pk, DevStatus* status) {
   if (status->failed) return;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x + (first ? *first : 0u);
   bool live = i < n_ub && i < *last;
+  if (!PACK && !live) return;
   if (live && keep && !keep[i]) {
     cellid[i] = CELL_DEAD;
     live = false;
+    if (!PACK) return;
   }
   uint64_t idx = 0;
   if (live) live = bin_one(g, i, pos[i], cellid, cell_count, cell_lo, cell_hi, status, idx);
-  if (pk.enabled) halo_pack_block<BIN_THREADS>(pk, live, i, (uint32_t)idx, status);  // (the whole block gets here)
+  if (PACK) halo_pack_block<BIN_THREADS>(pk, live, i, (uint32_t)idx, status);  // (the whole block gets here)
 }
 
 // ---------------------------------------------------------------------------------------------
