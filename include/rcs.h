@@ -238,6 +238,12 @@ int rcs_read_trace(rcs_sim* sim, uint64_t* ids, double* t_i, double* fx, double*
 /* 1 (default) = a step whose launch sequence repeats (nothing to upload, no trace, no kernel timing) is captured into a
  * CUDA graph the second time it comes up and is one graph launch from then on; 0 = always launch kernel by kernel. */
 #define RCS_OPT_GRAPHS 3u
+/* 1 = the kernels of a step are launched as programmatic dependents of one another
+ * (cudaLaunchAttributeProgrammaticStreamSerialization; every one of them starts with griddepcontrol.wait): the blocks of
+ * the next kernel are dispatched while the current one drains, so the launch latencies of the dozen kernels of a step
+ * overlap.  Same results.  Off by default: inside the captured graphs it was measured to change nothing at 2^24 agents and
+ * +-2 % either way on small crowds (profiles/r02_step_tile_kernel.md); RCS_PDL=1 in the environment turns the default on. */
+#define RCS_OPT_PDL 4u
 int rcs_set_option(rcs_sim* sim, uint32_t option, uint64_t value);
 
 /* ---- measurement helpers ---------------------------------------------------------------------- */

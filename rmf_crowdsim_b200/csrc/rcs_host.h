@@ -249,6 +249,7 @@ struct rcs_sim {
   uint32_t opt_bin_ahead = 0;  // RCS_OPT_BIN_AHEAD
   // CUDA graphs of steady-state steps
   uint32_t opt_graphs = 1;     // RCS_OPT_GRAPHS
+  uint32_t opt_pdl = 0;        // RCS_OPT_PDL
   uint64_t graph_epoch = 0;    // bumped by everything that can change a step's launch sequence or kernel arguments
   std::vector<rcs_host::StepGraph> step_graphs;
   rcs_host::StepKey recent_keys[2];  // keys of the last steps that ran eagerly (a key seen again is captured)

@@ -102,6 +102,7 @@ int rcs_sim_create(const rcs_sim_desc* desc, rcs_sim** out) {
 #undef CR_TRY
   s->stats.first_oob_id = ~0ull;
   if (const char* e = std::getenv("RCS_GRAPHS")) s->opt_graphs = std::atoi(e) != 0 ? 1u : 0u;  // default of RCS_OPT_GRAPHS
+  if (const char* e = std::getenv("RCS_PDL")) s->opt_pdl = std::atoi(e) != 0 ? 1u : 0u;        // default of RCS_OPT_PDL
   *out = s;
   return RCS_OK;
 }

@@ -73,6 +73,24 @@ static int ensure_stage(rcs_sim* s, uint64_t bytes) {
 }
 
 // exclusive scan of in[0..len) into out[0..len] (len+1 entries), optional cursor copy
+// Launch on the handle's stream -- with RCS_OPT_PDL as a programmatic dependent of the kernel enqueued before it: its
+// blocks may be dispatched while that kernel still runs, and the kernel's first statement, pdl_enter(), holds them
+// until it has completed (rcs_kernels.cuh).  Only kernels that start with pdl_enter() are launched through here.
+template <class... P, class... A>
+static void launch_dep(rcs_sim* s, void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, A&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s->stream;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = s->opt_pdl ? 1u : 0u;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+
 static int exclusive_scan(rcs_sim* s, const uint32_t* in, uint64_t len, uint32_t* out, uint32_t* cursor) {
   if (len == 0) {
     CU_TRY(s, cudaMemsetAsync(out, 0, sizeof(uint32_t), s->stream));
@@ -90,13 +108,13 @@ static int exclusive_scan(rcs_sim* s, const uint32_t* in, uint64_t len, uint32_t
   if (tiles <= 8192) {
     // the cell histogram of a step (4096 tiles at 2^24 cells): every block of the apply pass sums the tiles before
     // its own, a single tile needs no sums at all
-    if (tiles > 1) scan_reduce_kernel<<<(uint32_t)tiles, SCAN_THREADS, 0, s->stream>>>(in, len, s->tile_sums);
-    scan_apply_kernel<true><<<(uint32_t)tiles, SCAN_THREADS, 0, s->stream>>>(in, len, s->tile_sums, out, cursor);
+    if (tiles > 1) launch_dep(s, scan_reduce_kernel, (uint32_t)tiles, SCAN_THREADS, 0, in, len, s->tile_sums);
+    launch_dep(s, scan_apply_kernel<true>, (uint32_t)tiles, SCAN_THREADS, 0, in, len, s->tile_sums, out, cursor);
     s->launches += tiles > 1 ? 2 : 1;
   } else {
-    scan_reduce_kernel<<<(uint32_t)tiles, SCAN_THREADS, 0, s->stream>>>(in, len, s->tile_sums);
+    launch_dep(s, scan_reduce_kernel, (uint32_t)tiles, SCAN_THREADS, 0, in, len, s->tile_sums);
     scan_tile_sums_kernel<<<1, SCAN_THREADS, 0, s->stream>>>(s->tile_sums, (uint32_t)tiles, s->scan_total);
-    scan_apply_kernel<false><<<(uint32_t)tiles, SCAN_THREADS, 0, s->stream>>>(in, len, s->tile_sums, out, cursor);
+    launch_dep(s, scan_apply_kernel<false>, (uint32_t)tiles, SCAN_THREADS, 0, in, len, s->tile_sums, out, cursor);
     s->launches += 3;
   }
   CU_TRY(s, cudaGetLastError());
@@ -227,11 +245,11 @@ static int bin_agents(rcs_sim* s, uint32_t n_ub, const uint32_t* first, uint32_t
   }
   const uint32_t* dead = s->cur_has_dead ? s->keep : nullptr;
   if (pack)
-    bin_count_kernel<true><<<blocks_for(launch_n, BIN_THREADS), BIN_THREADS, 0, s->stream>>>(
+    launch_dep(s, bin_count_kernel<true>, blocks_for(launch_n, BIN_THREADS), BIN_THREADS, 0, 
         s->grid, n_ub, first, s->cnt + CNT_TOT, s->cur.pos, dead, s->cellid, s->cell_count, s->cell_lo, s->cell_hi, pk,
         s->d_status);
   else
-    bin_count_kernel<false><<<blocks_for(launch_n, BIN_THREADS), BIN_THREADS, 0, s->stream>>>(
+    launch_dep(s, bin_count_kernel<false>, blocks_for(launch_n, BIN_THREADS), BIN_THREADS, 0, 
         s->grid, n_ub, first, s->cnt + CNT_TOT, s->cur.pos, dead, s->cellid, s->cell_count, s->cell_lo, s->cell_hi, pk,
         s->d_status);
   s->launches += 1;
@@ -257,15 +275,15 @@ static int sort_into_srt(rcs_sim* s, uint32_t n_ub, bool clear_after_scan = fals
     if (rc) return rc;
   }
   if (n_ub) {
-    scatter_perm_kernel<<<blocks_for(n_ub, 256), 256, 0, s->stream>>>(n_ub, s->cnt + CNT_TOT, s->cellid, s->cursor,
+    launch_dep(s, scatter_perm_kernel, blocks_for(n_ub, 256), 256, 0, n_ub, s->cnt + CNT_TOT, s->cellid, s->cursor,
                                                                       s->perm, s->d_status);
     if (len)
-      sort_cells_by_id_kernel<<<blocks_for(len, 128), 128, 0, s->stream>>>(lo, hi, s->cell_start, s->cur.id, s->perm,
+      launch_dep(s, sort_cells_by_id_kernel, blocks_for(len, 128), 128, 0, lo, hi, s->cell_start, s->cur.id, s->perm,
                                                                            s->big_list, 4096, s->d_status);
-    sort_big_cells_kernel<<<148, 1024, 0, s->stream>>>(lo, hi, s->cell_start, s->cur.id, s->perm, s->slow_list,
+    launch_dep(s, sort_big_cells_kernel, 148, 1024, 0, lo, hi, s->cell_start, s->cur.id, s->perm, s->slow_list,
                                                        s->wide_list,
                                                        s->big_list, 4096, s->d_status);
-    gather_sorted_kernel<<<blocks_for(n_ub, GATHER_THREADS), GATHER_THREADS, 0, s->stream>>>(
+    launch_dep(s, gather_sorted_kernel, blocks_for(n_ub, GATHER_THREADS), GATHER_THREADS, 0, 
         n_ub, s->perm, s->cur, s->srt, s->cellid, s->strip.enabled ? s->srt_cell : nullptr, n_sorted_ptr(s),
         s->grid, s->cell_start, s->d_groups, s->d_groups ? s->slices : nullptr,
         s->d_groups ? s->tile_ranges : nullptr, s->d_status);
@@ -318,16 +336,16 @@ static void launch_step_kernel(rcs_sim* s, const StepArgs& a, uint32_t n_ub, boo
       s->tile_attr_set = true;
     }
     if (a.strip.enabled)
-      step_tile_kernel<true><<<blocks_for(n_ub, 32 * ST_WARPS), 32 * ST_WARPS, sizeof(TileShared), s->stream>>>(a);
+      launch_dep(s, step_tile_kernel<true>, blocks_for(n_ub, 32 * ST_WARPS), 32 * ST_WARPS, sizeof(TileShared), a);
     else
-      step_tile_kernel<false><<<blocks_for(n_ub, 32 * ST_WARPS), 32 * ST_WARPS, sizeof(TileShared), s->stream>>>(a);
-    step_aside_kernel<<<148 * 4, 32 * SW_WARPS, 0, s->stream>>>(a);
+      launch_dep(s, step_tile_kernel<false>, blocks_for(n_ub, 32 * ST_WARPS), 32 * ST_WARPS, sizeof(TileShared), a);
+    launch_dep(s, step_aside_kernel, 148 * 4, 32 * SW_WARPS, 0, a);
     s->launches += 2;
   } else if (sorted_input && s->opt_step_kernel != 1) {
     step_warp_kernel<<<blocks_for(n_ub, 32 * SW_WARPS), 32 * SW_WARPS, 0, s->stream>>>(a);
     // the agents it left aside (device-side lists): stencils wider than three columns or crowded columns go to
     // the chunked cooperative kernel, ids >= 2^53 and planners without the weight-0 proof to the sequential one
-    step_aside_kernel<<<148 * 4, 32 * SW_WARPS, 0, s->stream>>>(a);
+    launch_dep(s, step_aside_kernel, 148 * 4, 32 * SW_WARPS, 0, a);
     s->launches += 2;
   } else if (!sorted_input && s->opt_step_kernel != 1) {
     step_stream_kernel<<<blocks_for((n_ub + 1) / 2, 256), 256, 0, s->stream>>>(a);  // NoLocalPlan only, no churn

@@ -330,6 +330,11 @@ int rcs_set_option(rcs_sim* s, uint32_t option, uint64_t value) {
     s->graph_epoch += 1;
     return RCS_OK;
   }
+  if (option == RCS_OPT_PDL && value <= 1) {
+    s->opt_pdl = (uint32_t)value;
+    s->graph_epoch += 1;
+    return RCS_OK;
+  }
   if (option == RCS_OPT_BIN_AHEAD && value <= 1) {
     s->graph_epoch += 1;
     s->opt_bin_ahead = (uint32_t)value;

@@ -186,7 +186,7 @@ static int step_phase_a1(rcs_sim* s, double dt) {
   for (rcs_sim* nb : s->local_group)
     if (nb && nb != s && std::abs(nb->rank - s->rank) == 1 && nb->ev_copied)
       CU_TRY(s, cudaStreamWaitEvent(s->stream, nb->ev_copied, 0));
-  begin_step_kernel<<<1, 1, 0, s->stream>>>(s->d_status, s->cnt, s->strip.enabled ? s->send_l.buf.count : nullptr,
+  launch_dep(s, begin_step_kernel, 1, 1, 0, s->d_status, s->cnt, s->strip.enabled ? s->send_l.buf.count : nullptr,
                                             s->strip.enabled ? s->send_r.buf.count : nullptr,
                                             s->peer.enabled ? s->peer.xseq : nullptr);
   s->launches += 1;
@@ -283,7 +283,7 @@ static int step_phase_b(rcs_sim* s, double dt, uint32_t flags) {
       const HaloBuf& rl = s->peer.enabled ? s->peer.local[0] : s->recv_l.buf;
       const HaloBuf& rr = s->peer.enabled ? s->peer.local[1] : s->recv_r.buf;
       const uint32_t ghosts_ub = rl.cap + rr.cap;
-      halo_unpack_kernel<<<blocks_for(ghosts_ub, 256), 256, 0, s->stream>>>(
+      launch_dep(s, halo_unpack_kernel, blocks_for(ghosts_ub, 256), 256, 0, 
           s->cur, s->keep, (uint32_t)s->cap, rl, rr, has_l, has_r, s->cnt, s->d_status,
           s->peer.enabled ? s->peer.xseq : nullptr, s->grid, s->cellid, s->cell_count, s->cell_lo, s->cell_hi,
           s->send_l.buf.count, s->send_r.buf.count, s->peer.remote_hdr[0], s->peer.remote_hdr[1]);
@@ -350,7 +350,7 @@ static int step_phase_b(rcs_sim* s, double dt, uint32_t flags) {
       std::swap(s->cur.vel, s->srt.vel);
     }
   }
-  end_step_kernel<<<1, 1, 0, s->stream>>>(s->d_status, no_commit ? 0 : 1, s->d_steps_done,
+  launch_dep(s, end_step_kernel, 1, 1, 0, s->d_status, no_commit ? 0 : 1, s->d_steps_done,
                                           churned ? s->cnt + CNT_CUR : nullptr, n_sorted_ptr(s));
   s->launches += 1;
   CU_TRY(s, cudaGetLastError());

@@ -78,6 +78,17 @@ struct AgentArrays {
   double2* pv;  // host-planner preferred velocities; NaN in .x = None.  nullptr if no host planner exists
 };
 
+// Programmatic dependent launch (RCS_OPT_PDL): the kernels of a step are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the blocks of kernel k + 1 are dispatched while kernel k is
+// still running and sit in griddepcontrol.wait until k has completed and its stores are visible -- the launch latency
+// between the dozen small kernels of a step overlaps instead of adding up.  pdl_enter() is the FIRST statement of every
+// kernel launched that way, executed by every thread (a block that left without it would let its grid complete, and the
+// next grid start, before the previous one is done).  Without the launch attribute both instructions do nothing.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // Halo packing fused into the binning pass over the owned agents of a strip: an agent whose insert cell lies in
 // the outermost `width` columns is appended to the send buffer of that side (both, on a very narrow strip).
 struct PackArgs {
@@ -226,6 +237,7 @@ __global__ void __launch_bounds__(BIN_THREADS, 8) bin_count_kernel(
     GridDev g, uint32_t n_ub, const uint32_t* __restrict__ first, const uint32_t* __restrict__ last,
     const double2* __restrict__ pos, const uint32_t* __restrict__ keep, uint32_t* __restrict__ cellid,
     uint32_t* __restrict__ cell_count, uint64_t cell_lo, uint64_t cell_hi, PackArgs pk, DevStatus* status) {
+  pdl_enter();
   if (status->failed) return;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x + (first ? *first : 0u);
   bool live = i < n_ub && i < *last;
@@ -276,6 +288,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t& t
 }
 
 __global__ void scan_reduce_kernel(const uint32_t* __restrict__ in, uint64_t len, uint32_t* __restrict__ tile_sums) {
+  pdl_enter();
   uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
   uint32_t s = 0;
   if (base + SCAN_ITEMS <= len) {
@@ -317,6 +330,7 @@ template <bool RAW_SUMS>
 __global__ void scan_apply_kernel(const uint32_t* __restrict__ in, uint64_t len,
                                   const uint32_t* __restrict__ tile_sums, uint32_t* __restrict__ cell_start,
                                   uint32_t* __restrict__ cursor) {
+  pdl_enter();
   uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
   uint32_t v[SCAN_ITEMS];
   uint32_t s = 0;
@@ -379,6 +393,7 @@ __global__ void scan_apply_kernel(const uint32_t* __restrict__ in, uint64_t len,
 __global__ void scatter_perm_kernel(uint32_t n_ub, const uint32_t* __restrict__ n_ptr,
                                     const uint32_t* __restrict__ cellid, uint32_t* __restrict__ cursor,
                                     uint32_t* __restrict__ perm, const DevStatus* status) {
+  pdl_enter();
   if (status->failed) return;
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_ub || i >= *n_ptr) return;
@@ -394,6 +409,7 @@ __global__ void scatter_perm_kernel(uint32_t n_ub, const uint32_t* __restrict__ 
 __global__ void sort_cells_by_id_kernel(uint64_t cell_lo, uint64_t cell_hi, const uint32_t* __restrict__ cell_start,
                                         const uint64_t* __restrict__ id, uint32_t* __restrict__ perm,
                                         uint32_t* __restrict__ big_list, uint32_t big_cap, DevStatus* status) {
+  pdl_enter();
   if (status->failed) return;
   uint64_t c = cell_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cell_hi) return;
@@ -503,6 +519,7 @@ __global__ void __launch_bounds__(1024) sort_big_cells_kernel(uint64_t cell_lo, 
                                                               uint32_t* __restrict__ ranks,
                                                               const uint32_t* __restrict__ big_list, uint32_t big_cap,
                                                               DevStatus* status) {
+  pdl_enter();
   __shared__ unsigned long long skeys[BIG_SMEM_KEYS];
   __shared__ uint32_t partial[32][HUGE_ELEMS];
   __shared__ bool last_block;
@@ -601,6 +618,7 @@ __global__ void __launch_bounds__(GATHER_THREADS) gather_sorted_kernel(
     uint32_t* __restrict__ srt_cell, const uint32_t* __restrict__ n_sorted, GridDev g,
     const uint32_t* __restrict__ cell_start, const GroupDev* __restrict__ groups, uint4* __restrict__ slices,
     TileRange* __restrict__ tile_ranges, const DevStatus* status) {
+  pdl_enter();
   __shared__ uint32_t red[GATHER_THREADS / 32][6];
   if (status->failed) return;  // block-uniform
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1373,6 +1391,7 @@ __global__ void fill_f64_kernel(uint64_t n, double* p, double v) {
 // failed" (so that a failure reaches the neighbours with the next exchange and the whole job stops within `world` steps)
 __global__ void begin_step_kernel(DevStatus* st, uint32_t* cnt, uint32_t* send_l_hdr, uint32_t* send_r_hdr,
                                   uint32_t* xseq) {
+  pdl_enter();
   if (xseq) *xseq += 1u;  // peer-store transport: one exchange round per step, failed steps included
   if (send_l_hdr) {
     send_l_hdr[0] = 0u;
@@ -1406,6 +1425,7 @@ __global__ void begin_step_kernel(DevStatus* st, uint32_t* cnt, uint32_t* send_l
 // cnt_cur != nullptr on steps with churn: the state now holds *n_sorted entries (some flagged keep = 0).
 __global__ void end_step_kernel(DevStatus* st, int oob_fails, unsigned long long* steps_done, uint32_t* cnt_cur,
                                 const uint32_t* n_sorted) {
+  pdl_enter();
   if (st->failed) return;
   if ((oob_fails && st->oob_count) || st->halo_err || st->capacity_err) {
     st->local_failed = 1;
@@ -1641,6 +1661,7 @@ __global__ void halo_unpack_kernel(AgentArrays cur, uint32_t* __restrict__ keep,
                                    uint32_t* __restrict__ cell_count, uint64_t cell_lo, uint64_t cell_hi,
                                    const uint32_t* __restrict__ send_l_hdr, const uint32_t* __restrict__ send_r_hdr,
                                    uint32_t* remote_l_hdr, uint32_t* remote_r_hdr) {
+  pdl_enter();
   uint32_t par = 0u;
   if (xseq) {
     if (blockIdx.x == 0 && threadIdx.x < 2)  // this rank's own round first: nobody waits for a rank that waits
