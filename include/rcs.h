@@ -296,6 +296,10 @@ int rcs_dist_set_boundaries(rcs_sim* sim, int32_t world, const uint64_t* bounds)
  * the spawn-set all-reduce of source sinks. */
 int rcs_dist_peer_export(rcs_sim* sim, uint8_t out_handle[64]);
 int rcs_dist_peer_connect(rcs_sim* sim, const uint8_t* left_handle, const uint8_t* right_handle);
+/* Back to the NCCL transport (e.g. because rcs_dist_peer_connect failed on SOME rank -- no peer access between two of
+ * the GPUs -- and the host program has agreed on that over its own channel): every rank of the job calls it before
+ * the next step. */
+int rcs_dist_peer_disable(rcs_sim* sim);
 /* Column range [c0, c1) owned by `rank` of `world` for this handle's grid. */
 int rcs_dist_strip(rcs_sim* sim, int32_t rank, int32_t world, uint64_t* c0, uint64_t* c1);
 /* add_agents with caller-supplied global ids (the global sequential allocation of lib.rs:128-129

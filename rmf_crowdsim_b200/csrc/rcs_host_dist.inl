@@ -429,6 +429,16 @@ int rcs_dist_peer_connect(rcs_sim* s, const uint8_t* left_handle, const uint8_t*
   return RCS_OK;
 }
 
+int rcs_dist_peer_disable(rcs_sim* s) {
+  if (!s) return RCS_ERR_ARG;
+  CU_TRY(s, cudaSetDevice(s->device));
+  int rc = do_sync(s);
+  if (rc) return rc;
+  peer_teardown(s);  // back to ncclSend / ncclRecv
+  s->graph_epoch += 1;
+  return RCS_OK;
+}
+
 int rcs_dist_set_boundaries(rcs_sim* s, int32_t world, const uint64_t* bounds) {
   if (!s || world <= 0) return RCS_ERR_ARG;
   if (s->strip.enabled) {

@@ -8,6 +8,7 @@ kernels are tested on a single GPU.  Both give results that are bit-identical to
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -103,12 +104,25 @@ class StripSimulation(S.Simulation):
         self.c0, self.c1 = strip_columns(self, rank, world)
         self.transport = "nccl"
         if world > 1 and peer_gather is not None:
+            # every rank tries; the transport is used only if every rank could map both neighbours (the verdicts travel
+            # through the same gather), otherwise every rank goes back to ncclSend / ncclRecv
             mine = (C.c_uint8 * 64)()
-            N.check(self._h, self._lib.rcs_dist_peer_export(self._h, mine))
-            nb = [None if hd is None else (C.c_uint8 * 64).from_buffer_copy(hd)
-                  for hd in neighbour_handles(peer_gather(bytes(mine)), rank, world)]
-            N.check(self._h, self._lib.rcs_dist_peer_connect(self._h, nb[0], nb[1]))
-            self.transport = "peer stores"
+            ok = self._lib.rcs_dist_peer_export(self._h, mine) == N.RCS_OK
+            handles = peer_gather(bytes(mine) if ok else bytes(64))
+            if ok and all(any(hd) for hd in handles):
+                nb = [None if hd is None else (C.c_uint8 * 64).from_buffer_copy(hd)
+                      for hd in neighbour_handles(handles, rank, world)]
+                ok = self._lib.rcs_dist_peer_connect(self._h, nb[0], nb[1]) == N.RCS_OK
+            else:
+                ok = False
+            if os.environ.get("RCS_PEER_FAIL_RANK") == str(rank):  # test hook: this rank reports a failed mapping
+                ok = False
+            self.peer_error = "" if ok else (self._lib.rcs_last_error(self._h) or b"").decode()
+            verdicts = peer_gather(bytes([1 if ok else 0] * 64))
+            if all(v[0] == 1 for v in verdicts):
+                self.transport = "peer stores"
+            else:
+                N.check(self._h, self._lib.rcs_dist_peer_disable(self._h))
 
     def add_scene_agents(self, scene, ids: Optional[np.ndarray] = None, xy=None, vxy=None) -> int:
         """Adds the agents of `scene` (or of the given id / xy / vxy arrays) that fall into this strip."""
