@@ -186,7 +186,7 @@ static int step_spawn_set_nccl(rcs_sim* s) {
 }
 
 static int step_exchange_nccl(rcs_sim* s) {
-  if (s->world == 1 || s->peer.enabled) return RCS_OK;  // peer stores: halo_publish_kernel was the exchange
+  if (s->world == 1 || s->peer.enabled) return RCS_OK;  // peer stores: halo_unpack_kernel publishes and waits
   if (!s->nccl_comm) {
     s->err = "strip handle has no communicator";
     return RCS_ERR_NCCL;
