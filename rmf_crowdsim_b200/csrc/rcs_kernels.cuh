@@ -1622,10 +1622,10 @@ __global__ void ss_spawn_kernel(GridDev g, const SourceSinkDev* __restrict__ ss,
 // appends the ghosts of both received buffers after the owned agents; cnt[CNT_TOT] = owned + ghosts
 // ---- peer-store transport (one process per GPU, every GPU its own) ----------------------------------------------
 // The pack pass stores the boundary rows straight into the neighbour's receive buffer over NVLink (rcs_dist_peer_*:
-// the buffers are CUDA IPC mappings), halo_publish_kernel then writes count + failed flag and releases the round
-// number; the neighbour's halo_unpack_kernel acquires it.  Receive buffers have two halves used in turn: a rank
-// cannot publish round k + 2 before it has unpacked round k + 1, which its neighbour published after unpacking
-// round k -- so the half being written is never one still being read.
+// the buffers are CUDA IPC mappings); the next kernel on the stream, halo_unpack_kernel, first writes count + failed
+// flag behind them and releases the round number (halo_publish), then acquires the neighbours' rounds.  Receive
+// buffers have two halves used in turn: a rank packs round k + 2 only after it has unpacked round k + 1, which its
+// neighbour published only after it had unpacked round k -- so the half being written is never one still being read.
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
