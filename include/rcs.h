@@ -291,7 +291,7 @@ int rcs_dist_set_boundaries(rcs_sim* sim, int32_t world, const uint64_t* bounds)
  * program distributes the handles (e.g. torch.distributed.all_gather) and gives every rank its two neighbours'
  * (NULL where there is none) with rcs_dist_peer_connect.  From then on the binning pass stores the boundary columns
  * straight into the neighbour's memory over NVLink and a one-block kernel releases the round number the neighbour's
- * unpack kernel waits for (at most 30 s, then the step fails): no ncclSend / ncclRecv in the step, and a steady-state
+ * unpack kernel waits for (at most 120 s, then the step fails): no ncclSend / ncclRecv in the step, and a steady-state
  * step replays as one CUDA graph.  Every rank of the job must connect before the next step.  NCCL stays in use for
  * the spawn-set all-reduce of source sinks. */
 int rcs_dist_peer_export(rcs_sim* sim, uint8_t out_handle[64]);

@@ -1653,7 +1653,7 @@ __device__ __forceinline__ void halo_publish(uint32_t seq, const uint32_t* __res
   st_release_sys(dst + 2, seq);
 }
 
-constexpr unsigned long long HALO_WAIT_NS = 30ull * 1000000000ull;
+constexpr unsigned long long HALO_WAIT_NS = 120ull * 1000000000ull;
 
 __global__ void halo_unpack_kernel(AgentArrays cur, uint32_t* __restrict__ keep, uint32_t cap, HaloBuf left,
                                    HaloBuf right, int has_left, int has_right, uint32_t* cnt, DevStatus* status,
