@@ -161,7 +161,7 @@ def run(args) -> None:
         e2e = run_e2e(sim2, scene, min(K, 10), 3, dist, torch)
 
     if rank == 0:
-        from bench import ALGO_BYTES_NOLOCALPLAN, ALGO_BYTES_ZANLUNGO, measured_peaks, workload_name
+        from bench import ALGO_BYTES_NOLOCALPLAN, ALGO_BYTES_ZANLUNGO, kernel_counts, measured_peaks, workload_name
 
         peaks, how = measured_peaks()
         algo = ALGO_BYTES_NOLOCALPLAN if args.no_local_plan else ALGO_BYTES_ZANLUNGO
@@ -169,6 +169,12 @@ def run(args) -> None:
         value = n_live * K / (total_ms * 1e-3)
         k_ms = float(kmax.item())
         achieved = algo * (n_live / world) / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
+        # DRAM bytes of one rank's kernel launch: the single-GPU capture of the same workload, per agent, times the
+        # rank's agents (the strip form of the kernel moves 8 B per agent more: cell read, keep flag written)
+        counts = kernel_counts(f"{workload}_{args.variant}" + ("_nolp" if args.no_local_plan else ""))
+        traffic = None
+        if counts and counts.get("kernel_dram_bytes") and counts.get("agents"):
+            traffic = (counts["kernel_dram_bytes"] / counts["agents"] + 8.0) * (n_live / world)
         line = {
             "metric": "agent-steps/sec (query+Zanlungo+integrate)", "value": value, "unit": "agent-steps/s",
             "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": total_ms / K,
@@ -195,7 +201,9 @@ def run(args) -> None:
             "roofline": {
                 "bound": "hbm", "kernel": "step_tile_kernel (+ step_aside_kernel) per rank, slowest rank",
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "peak_source": how, "traffic": None,
+                "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "peak_source": how, "traffic": traffic,
+                "traffic_source": "profiles/kernel_counts.json (one-GPU ncu capture of this workload) per agent x agents "
+                                  "per rank + 8 B per agent of strip bookkeeping; not captured on this run",
                 "algorithmic_bytes_per_agent_step": algo, "kernel_ms": k_ms,
                 "kernel_share_of_step": k_ms * K / total_ms,
                 "note": "the Zanlungo kernel is FP64-pipe / latency bound, not HBM-bound (DESIGN.md)",
