@@ -85,3 +85,31 @@ def test_column_of_follows_the_saturating_cast():
     cx = column_of(x, -64.0, 2.0)
     assert list(cx[:8]) == [0, 0, 0, 1, 32, 32, 33, 0]
     assert cx[8] > 10**18
+
+
+def test_transport_selection_and_numa_binding_degrade_gracefully(monkeypatch):
+    """bench.py --gpus N: RCS_HALO=nccl selects the NCCL halo (no handle exchange at all); the NUMA binding of the e2e
+    buffers is a no-op where the GPU's node cannot be found (no NVML / sysfs entry: this container) and never raises."""
+    monkeypatch.setenv("RCS_HALO", "nccl")
+    assert DB.peer_gather(dist, torch) is None
+    monkeypatch.setenv("RCS_HALO", "peer")
+    assert callable(DB.peer_gather(dist, torch))
+    before = os.sched_getaffinity(0)
+    info = DB.bind_to_gpu_numa_node(0)
+    assert set(info) >= {"node", "cpus"}
+    if info["node"] is None:
+        assert os.sched_getaffinity(0) == before
+    else:
+        assert 0 < info["cpus"] <= len(before)
+    os.sched_setaffinity(0, before)
+    monkeypatch.setenv("RCS_NUMA", "0")
+    assert DB.bind_to_gpu_numa_node(0) == {"node": None, "cpus": None}
+
+
+def test_neighbour_handles_at_the_ends_of_the_strip_row():
+    hs = [bytes([r + 1] * 64) for r in range(4)]
+    assert neighbour_handles(hs, 0, 4) == (None, hs[1])
+    assert neighbour_handles(hs, 3, 4) == (hs[2], None)
+    assert neighbour_handles(hs, 2, 4) == (hs[1], hs[3])
+    with pytest.raises(AssertionError):
+        neighbour_handles(hs[:3], 0, 4)
